@@ -1,0 +1,190 @@
+/*
+ * libtdb200 -- C ABI of the B200-native (sm_100a) torch-darktable hot path.
+ *
+ * This header is the drop-in boundary.  It replaces the reference's pybind11/torch module
+ * `torch_darktable.torch_darktable_extension` (torch_darktable/csrc/extension.cpp:50-248) with plain
+ * `extern "C"` entry points: raw DEVICE pointers, sizes, scalars and a CUDA stream.  No torch types, no hidden
+ * allocation, no device synchronisation, no process-global device state.  The Python shim
+ * torch-darktable_b200/torch_darktable/extension.py presents the reference's attribute surface on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a TDB_E* code; tdb_last_error() gives a thread-local message.
+ *   - images are row-major, channels-last float32: CFA (H,W), RGB (H,W,3); byte buffers uint8.
+ *   - `filters` is the darktable CFA word (reference csrc/debayer/demosaic.h:7-12).
+ *   - `stream` is a cudaStream_t passed as void*; NULL = legacy default stream.
+ *   - pointers documented "device" must be device-accessible; scalars are passed by value (the reference
+ *     reads gains / sigmas / reduction results back with blocking .item() calls; here they stay on the device).
+ *   - workspaces ("scratch") are caller-provided; tdb_*_scratch_bytes() reports their size.
+ */
+#ifndef TDB200_H
+#define TDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDB_OK 0
+#define TDB_EINVAL 1   /* bad argument (maps to RuntimeError/ValueError in the shim) */
+#define TDB_ECUDA 2    /* CUDA runtime error (launch failure etc.) */
+#define TDB_EUNSUPPORTED 3
+
+#define TDB_FILTERS_RGGB 0x94949494u
+#define TDB_FILTERS_BGGR 0x16161616u
+#define TDB_FILTERS_GRBG 0x61616161u
+#define TDB_FILTERS_GBRG 0x49494949u
+
+typedef void *tdb_stream_t;
+
+int tdb_version(void);
+const char *tdb_last_error(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py's gpu_launches) */
+uint64_t tdb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * 12-bit packed codec.  Replaces decode12_float/half/u16, encode12_u16/float
+ * (extension.cpp:159-169, csrc/packed.cu:158-280).  npairs = pixels / 2 = bytes / 3.                       */
+int tdb_decode12_f32(const uint8_t *packed, float *out, int64_t npairs, int ids_format, int scaled, tdb_stream_t stream);
+int tdb_decode12_f16(const uint8_t *packed, uint16_t *out_half_bits, int64_t npairs, int ids_format, int scaled, tdb_stream_t stream);
+int tdb_decode12_u16(const uint8_t *packed, uint16_t *out, int64_t npairs, int ids_format, tdb_stream_t stream);
+int tdb_encode12_u16(const uint16_t *values, uint8_t *packed, int64_t npairs, int ids_format, tdb_stream_t stream);
+int tdb_encode12_f32(const float *values, uint8_t *packed, int64_t npairs, int ids_format, int scaled, tdb_stream_t stream);
+
+/* Fused ingest (north_star: unpack + black level + white balance in one pass; the reference runs
+ * decode12_float, then clone + apply_white_balance, pipeline/image_processor.py:190-240).
+ *   v = decode(p) / 4095;  v = v - black;  if gains: v = clamp(v * gains[fc(y,x)], 0, 1)
+ * black = 0 and gains = NULL reproduce decode12_float bit for bit.  gains: device float[3] or NULL.         */
+int tdb_unpack12_wb(const uint8_t *packed, float *cfa, int width, int height, int ids_format, uint32_t filters,
+                    float black, const float *gains, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * White balance.  Replaces apply_white_balance (extension.cpp:209, csrc/white_balance.cu:164-183).
+ * gains: device float[3].  in == out is allowed.                                                           */
+int tdb_white_balance(const float *in, float *out, int width, int height, uint32_t filters, const float *gains, tdb_stream_t stream);
+/* Replaces estimate_white_balance (extension.cpp:211, csrc/white_balance.cu:94-162): phase 1 collects the
+ * bright-patch samples; the quantile + mean run in the shim on the compacted device arrays.
+ * chroma: (n_samples,2), intensity: (n_samples), valid: (n_samples) uint8; n_samples = (W/stride)*(H/stride). */
+int tdb_wb_collect_samples(const float *cfa, int width, int height, uint32_t filters, int stride, float *chroma,
+                           float *intensity, uint8_t *valid, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Demosaic.  cfa (H,W) -> rgb (H,W,3).  width and height must be even and >= 16.
+ * tdb_bilinear5x5 replaces bilinear5x5_demosaic (extension.cpp:205, csrc/debayer/bilinear.cu:104-148).
+ * tdb_ppg replaces PPG.process (extension.cpp:57-65, csrc/debayer/ppg.cu:413-463); median_threshold in percent.
+ * tdb_rcd replaces RCD.process (extension.cpp:67-74, csrc/debayer/rcd.cu:601-671) with the semantics of a
+ *   FRESH reference workspace (the reference's dependence on the previous frame is not reproduced).
+ * The *_packed variants read the 12-bit packed frame directly and apply tdb_unpack12_wb's arithmetic on the fly. */
+int tdb_bilinear5x5(const float *cfa, float *rgb, int width, int height, uint32_t filters, tdb_stream_t stream);
+int tdb_ppg(const float *cfa, float *rgb, int width, int height, uint32_t filters, float median_threshold, tdb_stream_t stream);
+int tdb_rcd(const float *cfa, float *rgb, int width, int height, uint32_t filters, tdb_stream_t stream);
+
+#define TDB_DEMOSAIC_BILINEAR 0
+#define TDB_DEMOSAIC_PPG 1
+#define TDB_DEMOSAIC_RCD 2
+int tdb_demosaic_packed(const uint8_t *packed, float *rgb, int width, int height, int ids_format, uint32_t filters,
+                        int method, float black, const float *gains, float ppg_median_threshold, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Demosaic post-process.  Replaces PostProcess.process (extension.cpp:77-90, csrc/debayer/postprocess.cu:311-390):
+ * `passes` 3x3 median colour smoothing, global green equilibration (ratio computed on the device, no read-back),
+ * local green equilibration (threshold in percent).
+ * scratch: tdb_postprocess_scratch_bytes(width,height) bytes of device memory.                              */
+size_t tdb_postprocess_scratch_bytes(int width, int height);
+int tdb_postprocess(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
+                    int green_eq_local, int green_eq_global, float green_eq_threshold, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Colour ops (extension.cpp:127-156, csrc/color_conversions.cu, csrc/device_conversions.h).  npixels = H*W.  */
+#define TDB_RGB_TO_XYZ 0
+#define TDB_XYZ_TO_LAB 1
+#define TDB_LAB_TO_XYZ 2
+#define TDB_XYZ_TO_RGB 3
+#define TDB_RGB_TO_LAB 4
+#define TDB_LAB_TO_RGB 5
+#define TDB_MODIFY_HSL 6       /* p0..p2 = hue, sat, lum adjust */
+#define TDB_MODIFY_VIBRANCE 7  /* p0 = amount */
+int tdb_color_convert(const float *in, float *out, int64_t npixels, int op, float p0, float p1, float p2, tdb_stream_t stream);
+/* color_transform_3x3: out = clip(M * rgb); matrix: DEVICE float[9], row-major (the reference dereferences this
+ * device pointer on the host, csrc/color_conversions.cu:158-159, which faults; here it is read on the device). */
+int tdb_color_transform_3x3(const float *in, float *out, int64_t npixels, const float *matrix, tdb_stream_t stream);
+int tdb_compute_luminance(const float *rgb, float *lum, int64_t npixels, tdb_stream_t stream);
+int tdb_compute_log_luminance(const float *rgb, float *loglum, int64_t npixels, float eps, tdb_stream_t stream);
+int tdb_modify_luminance(const float *rgb, const float *lum, float *out, int64_t npixels, tdb_stream_t stream);
+int tdb_modify_log_luminance(const float *rgb, const float *loglum, float *out, int64_t npixels, float eps, tdb_stream_t stream);
+/* pipeline/util.py:8-10 normalize_image (a torch.compile'd helper in the reference): (rgb - b0) / (b1 - b0),
+ * bounds: device float[2].  nvalues = H*W*3. */
+int tdb_normalize(const float *in, float *out, int64_t nvalues, const float *bounds, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Image statistics (extension.cpp:182-185, csrc/tonemap/color_adaption.cu:90-166).  Accumulating calls so a
+ * list of images maps to one call per image on the same device accumulators, then one finalize.
+ *   bounds: device float[2], initialise with tdb_bounds_init (FLT_MAX, -FLT_MAX).
+ *   sums: device float[6] (log_gray, gray, r, g, b, valid count), zero-initialised by tdb_metrics_init.
+ *   tdb_metrics_finalize: metrics[5] = sums[0..4] / max(sums[5], 1).                                         */
+int tdb_bounds_init(float *bounds, tdb_stream_t stream);
+int tdb_bounds_accumulate(const float *rgb, int width, int height, int stride, float *bounds, tdb_stream_t stream);
+int tdb_metrics_init(float *sums, tdb_stream_t stream);
+int tdb_metrics_accumulate(const float *rgb, int width, int height, int stride, float min_gray, const float *bounds /* device float[2] or NULL = (0,1) */,
+                           float *sums, tdb_stream_t stream);
+int tdb_metrics_finalize(const float *sums, float *metrics, tdb_stream_t stream);
+/* a + (b - a) * t on n device floats (pipeline/util.py:4 lerp used for the EMA of bounds / metrics) */
+int tdb_lerp(const float *a, const float *b, float t, float *out, int n, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tone mapping -> uint8 (extension.cpp:188-195; csrc/tonemap/{reinhard,aces,linear}.cu, color_adaption.h).
+ * metrics: device float[5] (ignored for TDB_TM_ACES).  matrix: optional device float[9] colour matrix applied to
+ * the linear input first (north_star's fused 3x3; NULL = identity, which is what the reference pipeline does).
+ * transform: one of TDB_TF_* (pipeline/transform.py:39-56) fused into the store; out has the transformed shape. */
+#define TDB_TM_REINHARD 0
+#define TDB_TM_ACES 1
+#define TDB_TM_ADAPTIVE_ACES 2
+#define TDB_TM_LINEAR 3
+#define TDB_TF_NONE 0
+#define TDB_TF_ROTATE_90 1
+#define TDB_TF_ROTATE_180 2
+#define TDB_TF_ROTATE_270 3
+#define TDB_TF_TRANSPOSE 4
+#define TDB_TF_FLIP_HORIZ 5
+#define TDB_TF_FLIP_VERT 6
+#define TDB_TF_TRANSVERSE 7
+int tdb_tonemap(const float *rgb, uint8_t *out, int width, int height, int op, const float *metrics, float gamma,
+                float intensity, float light_adapt, float vibrance, const float *matrix, int transform, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Wiener tile denoiser.  Replaces Wiener.process (extension.cpp:215-223, csrc/denoise/denoise.cu:267-331).
+ * in/out (H,W,C), C in {1,3}; tile in {16,32}; overlap in {2,4,8}; sigmas: device float[C].
+ * scratch: tdb_wiener_scratch_bytes() bytes.
+ * tdb_wiener_log_luminance = Wiener.process_log_luminance (denoise.py:54-58) fused: log-luminance is computed
+ * while tiles are loaded and the Lab write-back happens in the normalisation pass; `noise` by value.        */
+size_t tdb_wiener_scratch_bytes(int width, int height, int channels, int tile);
+int tdb_wiener(const float *in, float *out, void *scratch, int width, int height, int channels, int tile, int overlap,
+               const float *sigmas, tdb_stream_t stream);
+int tdb_wiener_log_luminance(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap,
+                             float noise, float eps, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Bilateral-grid local contrast.  Replaces Bilateral.process (extension.cpp:111-121,
+ * csrc/local_contrast/bilateral.cu:358-385).  grid_size as the reference computes it (:273-299).
+ * scratch: 2 * gx*gy*gz floats (tdb_bilateral_scratch_bytes).
+ * tdb_bilateral_rgb = Bilateral.process_rgb (local_contrast.py:110-114) with compute_luminance fused into the
+ * splat and modify_luminance fused into the slice.                                                          */
+int tdb_bilateral_grid_size(int width, int height, float sigma_s, float sigma_r, int size[3]);
+size_t tdb_bilateral_scratch_bytes(int width, int height, float sigma_s, float sigma_r);
+int tdb_bilateral(const float *lum, float *out, void *scratch, int width, int height, float sigma_s, float sigma_r,
+                  float detail, tdb_stream_t stream);
+int tdb_bilateral_rgb(const float *rgb, float *out, void *scratch, int width, int height, float sigma_s, float sigma_r,
+                      float detail, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Local Laplacian.  Replaces Laplacian.process (extension.cpp:94-108, csrc/local_contrast/laplacian.cu:446-480),
+ * num_gamma = 6, fp16 storage like the reference.  scratch: tdb_laplacian_scratch_bytes().                  */
+size_t tdb_laplacian_scratch_bytes(int width, int height);
+int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int height, float sigma, float shadows,
+                  float highlights, float clarity, tdb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDB200_H */

@@ -1,0 +1,279 @@
+// Bilinear 5x5 and PPG demosaic as single fused shared-memory stencils.
+//
+// bilinear: replaces csrc/debayer/bilinear.cu (13 clamped global loads per pixel, 12-byte scattered stores).
+// PPG:      replaces the 3-4 kernel chain of csrc/debayer/ppg.cu:413-463 (border -> [pre-median] -> green -> red/blue,
+//           each a full HBM round trip plus a torch::zeros) by ONE kernel: the CFA patch is staged once (float plane or
+//           12-bit packed bytes), the optional median, the green plane and the red/blue fill all live in shared memory,
+//           and the RGB tile leaves through 128-bit stores.  Algorithmic traffic: 4 (or 1.5) B in + 12 B out per pixel.
+#include "cfa_tile.cuh"
+
+namespace tdb {
+namespace {
+
+constexpr int kTile = 32;      // output tile edge
+constexpr int kThreads = 256;  // 16 x 16 launch, 4 pixels per thread
+
+// ------------------------------------------------------------------------------------------------------------------
+// bilinear 5x5: weights are indexed by the pixel's position in the RGGB-ordered quad (0 = R site, 1 = G on an R row,
+// 2 = G on a B row, 3 = B site); taps outside the image use clamped coordinates (reference bilinear.cu:90).
+__constant__ int8_t kBilDx[13] = {-2, -1, -1, -1, 0, 0, 0, 0, 0, 1, 1, 1, 2};
+__constant__ int8_t kBilDy[13] = {0, -1, 0, 1, -2, -1, 0, 1, 2, -1, 0, 1, 0};
+__constant__ float kBilW[4][13][3] = {
+    {{0, -2, -3}, {0, 0, 4}, {0, 4, 0}, {0, 0, 4}, {0, -2, -3}, {0, 4, 0}, {16, 8, 12}, {0, 4, 0}, {0, -2, -3}, {0, 0, 4}, {0, 4, 0}, {0, 0, 4}, {0, -2, -3}},
+    {{-2, 0, 1}, {-2, 0, -2}, {8, 0, 0}, {-2, 0, -2}, {1, 0, -2}, {0, 0, 8}, {10, 16, 10}, {0, 0, 8}, {1, 0, -2}, {-2, 0, -2}, {8, 0, 0}, {-2, 0, -2}, {-2, 0, 1}},
+    {{1, 0, -2}, {-2, 0, -2}, {0, 0, 8}, {-2, 0, -2}, {-2, 0, 1}, {8, 0, 0}, {10, 16, 10}, {8, 0, 0}, {-2, 0, 1}, {-2, 0, -2}, {0, 0, 8}, {-2, 0, -2}, {1, 0, -2}},
+    {{-3, -2, 0}, {4, 0, 0}, {0, 4, 0}, {4, 0, 0}, {-3, -2, 0}, {0, 4, 0}, {12, 8, 16}, {0, 4, 0}, {-3, -2, 0}, {4, 0, 0}, {0, 4, 0}, {4, 0, 0}, {-3, -2, 0}}};
+
+// pixel type of quad position c = (x&1) + 2*(y&1); two bits per entry:
+// RGGB {0,1,2,3} = 0xE4, BGGR {3,1,2,0} = 0x27, GRBG {1,0,3,2} = 0xB1, GBRG {1,3,0,2} = 0x8D
+__device__ __forceinline__ int quad_type(uint32_t filters, int c) {
+  const uint32_t code = filters == TDB_FILTERS_RGGB ? 0xE4u : filters == TDB_FILTERS_BGGR ? 0x27u : filters == TDB_FILTERS_GRBG ? 0xB1u : 0x8Du;
+  return (code >> (2 * c)) & 3;
+}
+
+__global__ void __launch_bounds__(kThreads) bilinear_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
+                                                            uint32_t filters) {
+  constexpr int P = kTile + 4, S = P + 1;
+  __shared__ float patch[P * S];
+  __shared__ __align__(16) float outt[kTile * kTile * 3];
+  resolve_gains(src, filters);
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  stage_patch<Oob::kClamp, false>(patch, S, x0 - 2, y0 - 2, P, P, src, width, height);
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < kTile * kTile; i += kThreads) {
+    const int ly = i / kTile, lx = i - ly * kTile;
+    const int c = (lx & 1) + 2 * (ly & 1);  // tile origin is even in both axes
+    const int type = quad_type(filters, c);
+    float ar = 0.0f, ag = 0.0f, ab = 0.0f;
+    const float *center = patch + (ly + 2) * S + lx + 2;
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+      const float v = center[kBilDy[k] * S + kBilDx[k]];
+      ar = fmaf(kBilW[type][k][0], v, ar), ag = fmaf(kBilW[type][k][1], v, ag), ab = fmaf(kBilW[type][k][2], v, ab);
+    }
+    // every weight column sums to 16
+    outt[3 * i] = ar * 0.0625f, outt[3 * i + 1] = ag * 0.0625f, outt[3 * i + 2] = ab * 0.0625f;
+  }
+  __syncthreads();
+  store_rgb_tile(outt, kTile * 3, rgb, x0, y0, kTile, kTile, width, height);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// PPG.  Stages (all on shared memory, image coordinates in comments):
+//   cfa  : raw patch, halo 6 (4 without the median), zero outside the image
+//   med  : optional thresholded 9-tap same-colour median, halo 4                     (ppg.cu:21-113)
+//   tmp  : per-pixel RGB after border_interpolate(3) / green fill, halo 1            (ppg.cu:342-389, :120-223)
+//   out  : red/blue fill from tmp                                                    (ppg.cu:230-337)
+template <bool kMedian>
+__global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
+                                                       uint32_t filters, float threshold) {
+  constexpr int HC = kMedian ? 6 : 4;             // cfa halo
+  constexpr int PC = kTile + 2 * HC, SC = PC + 1; // cfa patch
+  constexpr int PM = kTile + 8, SM = PM + 1;      // median patch (halo 4)
+  constexpr int PT = kTile + 2;                   // tmp patch (halo 1)
+  extern __shared__ __align__(16) float smem[];
+  float *cfa = smem;                                    // PC*SC
+  float *med = cfa + PC * SC;                           // PM*SM (only with the median)
+  float *tmp = med + (kMedian ? PM * SM : 0);           // PT*PT*3
+  float *outt = tmp + PT * PT * 3;                      // kTile*kTile*3 (16-byte aligned by construction below)
+  outt = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(outt) + 15) & ~uintptr_t(15));
+
+  resolve_gains(src, filters);
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  stage_patch<Oob::kZero, false>(cfa, SC, x0 - HC, y0 - HC, PC, PC, src, width, height);
+  __syncthreads();
+
+  const float *g_in;  // plane the green stage reads, with halo 4 around the tile
+  int g_stride;
+  if (kMedian) {
+    constexpr int lim[5] = {0, 1, 2, 1, 0};
+    for (int i = tid; i < PM * PM; i += kThreads) {
+      const int my = i / PM, mx = i - my * PM;
+      const int x = x0 - 4 + mx, y = y0 - 4 + my;
+      float result = 0.0f;  // outside the image the next stage must see zeros (its own halo fill, ppg.cu:159)
+      if (x >= 0 && y >= 0 && x < width && y < height) {
+        const float *c = cfa + (my + 2) * SC + mx + 2;
+        const float center = c[0];
+        float v[9];
+        int cnt = 0, k = 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++)
+#pragma unroll
+          for (int j = -lim[r]; j <= lim[r]; j += 2) {
+            const float t = c[(r - 2) * SC + j];
+            if (fabsf(t - center) < threshold) v[k++] = t, cnt++;
+            else v[k++] = 64.0f + t;
+          }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int b = a + 1; b < 9; b++)
+            if (v[a] > v[b]) { const float t = v[a]; v[a] = v[b]; v[b] = t; }
+        float color = center;
+        if (fc(y, x, filters) & 1) {
+          // med[(cnt-1)/2] with a runtime index: select without local memory
+          const int want = (cnt == 1) ? 4 : (cnt - 1) / 2;
+          float target = v[0];
+#pragma unroll
+          for (int a = 1; a < 9; a++) target = (a == want) ? v[a] : target;
+          if (cnt == 1) target -= 64.0f;
+          color = center + fminf(fmaxf(target - center, -threshold), threshold);
+        }
+        result = fmaxf(color, 0.0f);
+      }
+      med[my * SM + mx] = result;
+    }
+    __syncthreads();
+    g_in = med, g_stride = SM;
+  } else {
+    g_in = cfa, g_stride = SC;  // HC == 4: same halo as the median patch
+  }
+
+  // tmp: border_interpolate for the outer 3 px ring, PPG green elsewhere
+  for (int i = tid; i < PT * PT; i += kThreads) {
+    const int ty = i / PT, tx = i - ty * PT;
+    const int x = x0 - 1 + tx, y = y0 - 1 + ty;
+    float r = 0.0f, g = 0.0f, b = 0.0f;  // zero outside the image (ppg.cu:270)
+    if (x >= 0 && y >= 0 && x < width && y < height) {
+      const int c = fc(y, x, filters);
+      if (x < 3 || y < 3 || x >= width - 3 || y >= height - 3) {
+        // 3x3 same-colour averages of the RAW cfa clamped at 0 (ppg.cu:342-389)
+        const float *p = cfa + (ty - 1 + HC) * SC + (tx - 1 + HC);
+        float sum[3] = {0, 0, 0};
+        int cnt[3] = {0, 0, 0};
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            const int xx = x + dx, yy = y + dy;
+            if (xx >= 0 && yy >= 0 && xx < width && yy < height) {
+              const int f = fc(yy, xx, filters);
+              const float v = fmaxf(0.0f, p[dy * SC + dx]);
+              sum[0] += f == 0 ? v : 0.0f, sum[1] += f == 1 ? v : 0.0f, sum[2] += f == 2 ? v : 0.0f;
+              cnt[0] += f == 0, cnt[1] += f == 1, cnt[2] += f == 2;
+            }
+          }
+        const float v = fmaxf(0.0f, p[0]);
+        r = cnt[0] > 0 ? sum[0] / cnt[0] : v;
+        g = cnt[1] > 0 ? sum[1] / cnt[1] : v;
+        b = cnt[2] > 0 ? sum[2] / cnt[2] : v;
+        if (c == 0) r = v; else if (c == 2) b = v; else g = v;
+      } else {
+        const float *p = g_in + (ty - 1 + 4) * g_stride + (tx - 1 + 4);
+        const float pc = p[0];
+        if (c == 0) r = pc; else if (c == 2) b = pc; else g = pc;
+        if (c != 1) {
+          const float pym = p[-g_stride], pym2 = p[-2 * g_stride], pym3 = p[-3 * g_stride];
+          const float pyM = p[g_stride], pyM2 = p[2 * g_stride], pyM3 = p[3 * g_stride];
+          const float pxm = p[-1], pxm2 = p[-2], pxm3 = p[-3], pxM = p[1], pxM2 = p[2], pxM3 = p[3];
+          const float guessx = (pxm + pc + pxM) * 2.0f - pxM2 - pxm2;
+          const float diffx = (fabsf(pxm2 - pc) + fabsf(pxM2 - pc) + fabsf(pxm - pxM)) * 3.0f + (fabsf(pxM3 - pxM) + fabsf(pxm3 - pxm)) * 2.0f;
+          const float guessy = (pym + pc + pyM) * 2.0f - pyM2 - pym2;
+          const float diffy = (fabsf(pym2 - pc) + fabsf(pyM2 - pc) + fabsf(pym - pyM)) * 3.0f + (fabsf(pyM3 - pyM) + fabsf(pym3 - pym)) * 2.0f;
+          if (diffx > diffy) g = fmaxf(fminf(guessy * 0.25f, fmaxf(pym, pyM)), fminf(pym, pyM));
+          else g = fmaxf(fminf(guessx * 0.25f, fmaxf(pxm, pxM)), fminf(pxm, pxM));
+        }
+        r = fmaxf(r, 0.0f), g = fmaxf(g, 0.0f), b = fmaxf(b, 0.0f);
+      }
+    }
+    tmp[3 * i] = r, tmp[3 * i + 1] = g, tmp[3 * i + 2] = b;
+  }
+  __syncthreads();
+
+  // red / blue fill
+  for (int i = tid; i < kTile * kTile; i += kThreads) {
+    const int ly = i / kTile, lx = i - ly * kTile;
+    const int x = x0 + lx, y = y0 + ly;
+    const float *p = tmp + 3 * ((ly + 1) * PT + lx + 1);
+    float r = p[0], g = p[1], b = p[2];
+    if (x < width && y < height && !(x == 0 || y == 0 || x == width - 1 || y == height - 1)) {
+      const int c = fc(y, x, filters);
+      constexpr int R = 3 * PT;  // one tmp row
+      if (c == 1) {
+        const float *nt = p - R, *nb = p + R, *nl = p - 3, *nr = p + 3;
+        if (fc(y, x + 1, filters) == 0) {
+          b = (nt[2] + nb[2] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
+          r = (nl[0] + nr[0] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
+        } else {
+          r = (nt[0] + nb[0] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
+          b = (nl[2] + nr[2] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
+        }
+      } else {
+        const float *ntl = p - R - 3, *ntr = p - R + 3, *nbl = p + R - 3, *nbr = p + R + 3;
+        const int k = (c == 0) ? 2 : 0;
+        const float diff1 = fabsf(ntl[k] - nbr[k]) + fabsf(ntl[1] - g) + fabsf(nbr[1] - g);
+        const float guess1 = ntl[k] + nbr[k] + 2.0f * g - ntl[1] - nbr[1];
+        const float diff2 = fabsf(ntr[k] - nbl[k]) + fabsf(ntr[1] - g) + fabsf(nbl[1] - g);
+        const float guess2 = ntr[k] + nbl[k] + 2.0f * g - ntr[1] - nbl[1];
+        const float v = diff1 > diff2 ? guess2 * 0.5f : (diff1 < diff2 ? guess1 * 0.5f : (guess1 + guess2) * 0.25f);
+        if (c == 0) b = v; else r = v;
+      }
+    }
+    outt[3 * i] = fmaxf(r, 0.0f), outt[3 * i + 1] = fmaxf(g, 0.0f), outt[3 * i + 2] = fmaxf(b, 0.0f);
+  }
+  __syncthreads();
+  store_rgb_tile(outt, kTile * 3, rgb, x0, y0, kTile, kTile, width, height);
+}
+
+template <bool kMedian>
+constexpr size_t ppg_smem_bytes() {
+  constexpr int HC = kMedian ? 6 : 4, PC = kTile + 2 * HC, SC = PC + 1, PM = kTile + 8, SM = PM + 1, PT = kTile + 2;
+  return sizeof(float) * (PC * SC + (kMedian ? PM * SM : 0) + PT * PT * 3 + kTile * kTile * 3) + 16;
+}
+
+int check_frame(const char *name, int width, int height) {
+  if (width < 16 || height < 16 || (width & 1) || (height & 1)) {
+    set_error("%s: width and height must be even and >= 16 (got %dx%d)", name, width, height);
+    return TDB_EINVAL;
+  }
+  return TDB_OK;
+}
+
+}  // namespace
+
+int launch_bilinear(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, cudaStream_t s) {
+  dim3 block(16, 16), grid(div_up(width, kTile), div_up(height, kTile));
+  bilinear_kernel<<<grid, block, 0, s>>>(src, rgb, width, height, filters);
+  return check_launch("bilinear5x5_demosaic");
+}
+
+int launch_ppg(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, float median_threshold, cudaStream_t s) {
+  dim3 block(16, 16), grid(div_up(width, kTile), div_up(height, kTile));
+  if (median_threshold > 0.0f) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(ppg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppg_smem_bytes<true>());
+      attr = true;
+    }
+    ppg_kernel<true><<<grid, block, ppg_smem_bytes<true>(), s>>>(src, rgb, width, height, filters, median_threshold / 100.0f);
+  } else {
+    ppg_kernel<false><<<grid, block, ppg_smem_bytes<false>(), s>>>(src, rgb, width, height, filters, 0.0f);
+  }
+  return check_launch("ppg_demosaic");
+}
+
+}  // namespace tdb
+
+using namespace tdb;
+
+extern "C" {
+
+int tdb_bilinear5x5(const float *cfa, float *rgb, int width, int height, uint32_t filters, tdb_stream_t stream) {
+  TDB_REQUIRE(cfa && rgb, "bilinear5x5_demosaic: null pointer");
+  if (int e = check_frame("bilinear5x5_demosaic", width, height)) return e;
+  CfaSource src{};
+  src.cfa = cfa;
+  return launch_bilinear(src, rgb, width, height, filters, as_stream(stream));
+}
+
+int tdb_ppg(const float *cfa, float *rgb, int width, int height, uint32_t filters, float median_threshold, tdb_stream_t stream) {
+  TDB_REQUIRE(cfa && rgb, "PPG: null pointer");
+  if (int e = check_frame("PPG", width, height)) return e;
+  CfaSource src{};
+  src.cfa = cfa;
+  return launch_ppg(src, rgb, width, height, filters, median_threshold, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Shared host/device helpers of libtdb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/tdb200.h"
+
+namespace tdb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
+void count_launches(int n);
+
+#define TDB_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::tdb::set_error(__VA_ARGS__);  \
+      return TDB_EINVAL;              \
+    }                                 \
+  } while (0)
+
+static inline cudaStream_t as_stream(tdb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- CFA helpers ------------------------------------------------------------------------------------------
+// colour of a CFA site: 0 = R, 1 = G, 2 = B (the four supported filter words never yield 3)
+__host__ __device__ __forceinline__ int fc(int row, int col, uint32_t filters) {
+  return (filters >> ((((row << 1) & 14) + (col & 1)) << 1)) & 3u;
+}
+
+// ---- packed 12-bit pairs ---------------------------------------------------------------------------------
+// three bytes b0,b1,b2 (little end of `w`) -> two 12-bit samples
+template <bool kIds>
+__device__ __forceinline__ void unpack_pair(uint32_t w, uint32_t &p0, uint32_t &p1) {
+  const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu;
+  if (kIds) {
+    p0 = (b0 << 4) | (b2 & 0xfu);
+    p1 = (b1 << 4) | (b2 >> 4);
+  } else {
+    p0 = ((b1 & 0xfu) << 8) | b0;
+    p1 = (b2 << 4) | (b1 >> 4);
+  }
+}
+
+template <bool kIds>
+__device__ __forceinline__ uint32_t pack_pair(uint32_t p0, uint32_t p1) {
+  if (kIds) return (p0 >> 4) | ((p1 >> 4) << 8) | ((((p0 & 0xfu) << 4) | (p1 & 0xfu)) << 16);
+  return (p0 & 0xffu) | ((((p1 & 0xfu) << 4) | (p0 >> 8)) << 8) | ((p1 >> 4) << 16);
+}
+
+// sample `i` (0-based) of a packed stream through byte loads; used on halo / unaligned paths only
+template <bool kIds>
+__device__ __forceinline__ uint32_t packed_sample(const uint8_t *__restrict__ p, int64_t i) {
+  const uint8_t *b = p + (i >> 1) * 3;
+  const uint32_t w = (uint32_t)__ldg(b) | ((uint32_t)__ldg(b + 1) << 8) | ((uint32_t)__ldg(b + 2) << 16);
+  uint32_t p0, p1;
+  unpack_pair<kIds>(w, p0, p1);
+  return (i & 1) ? p1 : p0;
+}
+
+// ---- small math ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ float sqr(float x) { return x * x; }
+__device__ __forceinline__ float mixf(float a, float b, float t) { return (1.0f - t) * a + t * b; }
+
+// streaming 128-bit accesses that do not pollute L1 (data is touched once)
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void st_stream(uint4 *p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// float atomic min / max through the ordered-int trick (no CAS loop)
+__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace tdb

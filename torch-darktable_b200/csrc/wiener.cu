@@ -1,0 +1,385 @@
+// Overlapped-tile Wiener denoiser (FFT domain shrinkage) with register-resident FFTs.
+//
+// Reference (csrc/denoise/denoise.cu:191-242, fft.h): one CTA of KxK threads per tile, one pixel per thread, radix-2
+// FFT by warp shuffles (2 shuffles per butterfly), shared-memory transposes, two global float atomics per tile pixel
+// (value + weight mask) into a padded accumulator, sigmas / windows in process-global __constant__ symbols.
+// Every pixel is covered by overlap^2 tiles, so at K=32/overlap 4 the stage is arithmetic-bound, not HBM-bound.
+//
+// Here ONE WARP owns TWO real tiles packed as a single complex tile z = a + i*b:
+//   lane = column, registers = rows; column FFT in registers (radix-2 DIF, compile-time twiddles, no shuffles),
+//   transpose through shared memory, row FFT in registers; the two spectra are separated with the Hermitian identity
+//   A = (Z + conj(Z~))/2, B = (Z - conj(Z~))/(2i) (one shuffle per value), shrunk with their own Wiener gains, merged
+//   again, and taken back through the inverse (DIT) transforms.  Half the FFT work of the reference, no shuffles inside
+//   the butterflies, coalesced loads and stores (a warp touches 32 consecutive pixels of a row at a time).
+//   The weight mask is separable and input-independent, so it is evaluated in closed form in the normalisation pass
+//   instead of being accumulated with atomics; the accumulator has no padding.
+// No process-global device state: windows and sigmas travel as kernel arguments.
+#include <cmath>
+
+#include "color_math.cuh"
+
+namespace tdb {
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr float kEps = 1e-15f;
+
+// cos/sin(2*pi*k/32), k = 0..15, as literals so that unrolled butterflies fold them into immediates
+__device__ __forceinline__ constexpr float tw_cos32(int k) {
+  switch (k) {
+    case 0: return 1.0f; case 1: return 0.98078528040323043f; case 2: return 0.92387953251128674f; case 3: return 0.83146961230254524f;
+    case 4: return 0.70710678118654757f; case 5: return 0.55557023301960218f; case 6: return 0.38268343236508978f;
+    case 7: return 0.19509032201612825f; case 8: return 0.0f; case 9: return -0.19509032201612825f; case 10: return -0.38268343236508978f;
+    case 11: return -0.55557023301960218f; case 12: return -0.70710678118654757f; case 13: return -0.83146961230254524f;
+    case 14: return -0.92387953251128674f; default: return -0.98078528040323043f;
+  }
+}
+__device__ __forceinline__ constexpr float tw_sin32(int k) { return k < 8 ? tw_cos32(8 - k) : tw_cos32(k - 8); }  // sin(x) = cos(pi/2 - x)
+
+// forward DIF radix-2: natural order in, bit-reversed order out.  W = exp(-2*pi*i/N)
+template <int N>
+__device__ __forceinline__ void fft_dif(float (&re)[N], float (&im)[N]) {
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int s = 0; s < N; s += 2 * half) {
+#pragma unroll
+      for (int k = 0; k < half; k++) {
+        const int a = s + k, b = s + k + half;
+        const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
+        re[a] = ar + br, im[a] = ai + bi;
+        const float dr = ar - br, di = ai - bi;
+        const int t = k * (16 / half);  // twiddle index on the 32-point circle
+        if (t == 0) {
+          re[b] = dr, im[b] = di;
+        } else if (t == 8) {  // multiply by -i
+          re[b] = di, im[b] = -dr;
+        } else {
+          const float c = tw_cos32(t), sn = tw_sin32(t);  // (dr + i di) * (c - i sn)
+          re[b] = dr * c + di * sn, im[b] = di * c - dr * sn;
+        }
+      }
+    }
+  }
+}
+
+// inverse DIT radix-2: bit-reversed order in, natural order out, unscaled.  W = exp(+2*pi*i/N)
+template <int N>
+__device__ __forceinline__ void fft_dit_inv(float (&re)[N], float (&im)[N]) {
+#pragma unroll
+  for (int half = 1; half < N; half <<= 1) {
+#pragma unroll
+    for (int s = 0; s < N; s += 2 * half) {
+#pragma unroll
+      for (int k = 0; k < half; k++) {
+        const int a = s + k, b = s + k + half;
+        const int t = k * (16 / half);
+        float tr, ti;
+        if (t == 0) {
+          tr = re[b], ti = im[b];
+        } else if (t == 8) {  // multiply by +i
+          tr = -im[b], ti = re[b];
+        } else {
+          const float c = tw_cos32(t), sn = tw_sin32(t);  // (br + i bi) * (c + i sn)
+          tr = re[b] * c - im[b] * sn, ti = im[b] * c + re[b] * sn;
+        }
+        const float ar = re[a], ai = im[a];
+        re[a] = ar + tr, im[a] = ai + ti;
+        re[b] = ar - tr, im[b] = ai - ti;
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ constexpr int brev(int v) {
+  int r = 0;
+  for (int b = 1; b < K; b <<= 1) r = (r << 1) | ((v & b) ? 1 : 0);
+  return r;
+}
+
+// transpose a KxK complex block held as (lane = j, register = i) into (lane = i, register = j) through shared memory
+template <int K>
+__device__ __forceinline__ void transpose(float (&re)[K], float (&im)[K], float *sre, float *sim, int lane_in) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < K; i++) sre[lane_in * (K + 1) + i] = re[i], sim[lane_in * (K + 1) + i] = im[i];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < K; i++) re[i] = sre[i * (K + 1) + lane_in], im[i] = sim[i * (K + 1) + lane_in];
+}
+
+__device__ __forceinline__ int reflect_index(int x, int limit) {
+  if (x < 0) x = -x;
+  if (x >= limit) x = 2 * limit - x - 1;
+  // the reference reads out of bounds here when a side is shorter than 2K-1; stay defined instead
+  return min(max(x, 0), limit - 1);
+}
+
+struct WienerArgs {
+  const float *in;     // (H, W, C)
+  float *acc;          // (H, W, C) accumulator, zeroed by the caller
+  const float *sigmas; // device float[C], or null when sigma_value is used
+  float sigma_value;
+  int width, height, channels;
+  int stride;          // K / overlap
+  int grid_w, grid_h;  // tiles per row / column
+  int pairs_w;         // tile pairs per row
+  int64_t njobs;       // grid_h * pairs_w * channels
+  float win[32];       // 1-D window (both the FFT and the interpolation window of the reference)
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) wiener_tile_kernel(const WienerArgs a) {
+  constexpr int SUB = 32 / K;  // tile pairs handled by one warp at a time
+  extern __shared__ float s_t[];  // [kWarps * SUB][2][K * (K + 1)] transpose staging (dynamic: 66 KB at K = 32)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / K, c = lane % K;  // c = this lane's column inside the tile
+  float *sre = s_t + (size_t)(warp * SUB + sub) * 2 * K * (K + 1), *sim = sre + K * (K + 1);
+  const float wc = a.win[c];
+  const unsigned sub_mask = SUB == 1 ? 0xffffffffu : (0xffffu << (16 * sub));
+  // lane holding frequency -kx after the row/column exchange: registers/lane indices are in bit-reversed order
+  const int partner_lane = sub * K + brev<K>((K - brev<K>(c)) & (K - 1));
+
+  const int64_t job0 = ((int64_t)blockIdx.x * kWarps + warp) * SUB + sub;
+  const int64_t job_step = (int64_t)gridDim.x * kWarps * SUB;
+  // all lanes of a warp must run the same number of iterations (shuffles / __syncwarp inside)
+  const int64_t iters = (a.njobs + job_step - 1) / job_step;
+  for (int64_t it = 0; it < iters; it++) {
+    const int64_t job = job0 + it * job_step;
+    const bool live = job < a.njobs;
+    int ch = 0, gy = 0, px = 0;
+    if (live) {
+      ch = (int)(job % a.channels);
+      const int64_t t = job / a.channels;
+      px = (int)(t % a.pairs_w), gy = (int)(t / a.pairs_w);
+    }
+    const int shift = K / a.stride;  // the tile grid starts one tile early (denoise.cu:146)
+    const int oy = (gy - shift) * a.stride;
+    const int ox0 = (2 * px - shift) * a.stride, ox1 = (2 * px + 1 - shift) * a.stride;
+    const bool has_b = live && (2 * px + 1) < a.grid_w;
+
+    float re[K], im[K];
+    float sum_a = 0.0f, sum_b = 0.0f;
+    {
+      const int xa = reflect_index(ox0 + c, a.width), xb = reflect_index(ox1 + c, a.width);
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const int y = reflect_index(oy + r, a.height);
+        const float va = live ? __ldg(a.in + ((int64_t)y * a.width + xa) * a.channels + ch) : 0.0f;
+        const float vb = has_b ? __ldg(a.in + ((int64_t)y * a.width + xb) * a.channels + ch) : 0.0f;
+        re[r] = va, im[r] = vb;
+        sum_a += va, sum_b += vb;
+      }
+    }
+#pragma unroll
+    for (int o = K / 2; o > 0; o >>= 1) {
+      sum_a += __shfl_xor_sync(sub_mask, sum_a, o);
+      sum_b += __shfl_xor_sync(sub_mask, sum_b, o);
+    }
+    const float mean_a = sum_a / (float)(K * K), mean_b = sum_b / (float)(K * K);
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+      const float w = a.win[r] * wc;  // reference: window_fft[pos.x] * window_fft[pos.y]
+      re[r] = (re[r] - mean_a) * w, im[r] = (im[r] - mean_b) * w;
+    }
+
+    fft_dif<K>(re, im);                          // along y (registers)
+    transpose<K>(re, im, sre, sim, c);           // lane = ky (bit-reversed), registers = x
+    fft_dif<K>(re, im);                          // along x
+
+    // separate the two real-input spectra, apply the Wiener gain to each, merge  (apply_gain: denoise.cu:181-185)
+    {
+      const float sg = a.sigmas ? __ldg(a.sigmas + ch) : a.sigma_value;
+      const float s2 = sg * sg;
+      // register p holds kx = brev(p); its mirror -kx sits in register brev((K - brev(p)) % K)
+#pragma unroll
+      for (int p = 0; p < K; p++) {
+        const int q = brev<K>((K - brev<K>(p)) & (K - 1));
+        if (q < p) continue;  // handled together with its mirror
+        const float zr_p = re[p], zi_p = im[p], zr_q = re[q], zi_q = im[q];
+        // mirrored bin of (lane, p) is (partner_lane, q) and vice versa
+        const float mr_p = __shfl_sync(sub_mask, zr_q, partner_lane), mi_p = __shfl_sync(sub_mask, zi_q, partner_lane);
+        const float mr_q = __shfl_sync(sub_mask, zr_p, partner_lane), mi_q = __shfl_sync(sub_mask, zi_p, partner_lane);
+        {
+          const float ar = 0.5f * (zr_p + mr_p), ai = 0.5f * (zi_p - mi_p);
+          const float br = 0.5f * (zi_p + mi_p), bi = -0.5f * (zr_p - mr_p);
+          const float pa = ar * ar + ai * ai + kEps, pb = br * br + bi * bi + kEps;
+          const float ga = fmaxf(pa - s2, 0.0f) / pa, gb = fmaxf(pb - s2, 0.0f) / pb;
+          re[p] = ga * ar - gb * bi, im[p] = ga * ai + gb * br;
+        }
+        if (q != p) {
+          const float ar = 0.5f * (zr_q + mr_q), ai = 0.5f * (zi_q - mi_q);
+          const float br = 0.5f * (zi_q + mi_q), bi = -0.5f * (zr_q - mr_q);
+          const float pa = ar * ar + ai * ai + kEps, pb = br * br + bi * bi + kEps;
+          const float ga = fmaxf(pa - s2, 0.0f) / pa, gb = fmaxf(pb - s2, 0.0f) / pb;
+          re[q] = ga * ar - gb * bi, im[q] = ga * ai + gb * br;
+        }
+      }
+    }
+
+    fft_dit_inv<K>(re, im);                      // along x
+    transpose<K>(re, im, sre, sim, c);           // lane = x, registers = ky (bit-reversed)
+    fft_dit_inv<K>(re, im);                      // along y
+
+    // overlap-add: (value + mean * w_fft) * w_interp   (store_pixel, denoise.cu:150-178)
+    const float inv = 1.0f / (float)(K * K);
+    const int xa = ox0 + c, xb = ox1 + c;
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+      const int y = oy + r;
+      if (y < 0 || y >= a.height) continue;
+      const float w = a.win[r] * wc;
+      if (live && xa >= 0 && xa < a.width) atomicAdd(a.acc + ((int64_t)y * a.width + xa) * a.channels + ch, (re[r] * inv + mean_a * w) * w);
+      if (has_b && xb >= 0 && xb < a.width) atomicAdd(a.acc + ((int64_t)y * a.width + xb) * a.channels + ch, (im[r] * inv + mean_b * w) * w);
+    }
+  }
+}
+
+// closed-form weight mask: sum over the overlap^2 covering tiles of (w_fft * w_interp)(x) * (w_fft * w_interp)(y)
+struct NormArgs {
+  const float *acc;
+  const float *rgb;  // only for the log-luminance composite
+  float *out;
+  int width, height, channels, K, stride;
+  float win[32];
+};
+
+template <bool kLogLum>
+__global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a) {
+  __shared__ float m1[32];  // 1-D mask factor per phase: sum_j win[r + j*stride]^2
+  if (threadIdx.x < a.stride) {
+    float s = 0.0f;
+    for (int j = threadIdx.x; j < a.K; j += a.stride) s += a.win[j] * a.win[j];
+    m1[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const int64_t n = (int64_t)a.width * a.height;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / a.width), x = (int)(i - (int64_t)y * a.width);
+    const float mask = m1[x % a.stride] * m1[y % a.stride];
+    if (kLogLum) {
+      const float l = __ldg(a.acc + i) / (mask + kEps);
+      const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
+      const rgb_t r = pub::with_luminance(c, expf(l));
+      a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
+    } else {
+      for (int ch = 0; ch < a.channels; ch++) a.out[i * a.channels + ch] = __ldg(a.acc + i * a.channels + ch) / (mask + kEps);
+    }
+  }
+}
+
+struct LogLum {
+  float eps;
+  __device__ float operator()(rgb_t c) const { return logf(fmaxf(eps, pub::luminance(c))); }
+};
+__global__ void __launch_bounds__(256) loglum_kernel(const float *__restrict__ rgb, float *__restrict__ out, int64_t n, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = LogLum{eps}(rgb_t{__ldg(rgb + 3 * i), __ldg(rgb + 3 * i + 1), __ldg(rgb + 3 * i + 2)});
+}
+
+// the reference builds the windows with torch (float32): linspace, exp(-r^2/scale), divide by the L2 norm (window.h:18-43)
+void make_window(int K, float *win) {
+  const float half = K / 2.0f, scale = 0.3f * half * half;
+  float norm2 = 0.0f;
+  for (int i = 0; i < K; i++) {
+    const float r = (-half + 0.5f) + (float)i;
+    win[i] = expf(-(r * r) / scale);
+    norm2 += win[i] * win[i];
+  }
+  const float norm = sqrtf(norm2);
+  for (int i = 0; i < K; i++) win[i] /= norm;
+  for (int i = K; i < 32; i++) win[i] = 0.0f;
+}
+
+int run_tiles(const float *in, float *acc, int width, int height, int channels, int tile, int overlap, const float *sigmas,
+              float sigma_value, cudaStream_t s) {
+  WienerArgs a{};
+  a.in = in, a.acc = acc, a.sigmas = sigmas, a.sigma_value = sigma_value;
+  a.width = width, a.height = height, a.channels = channels;
+  a.stride = tile / overlap;
+  const int start = tile / a.stride;
+  a.grid_h = (height + tile + a.stride - 1) / a.stride + start;
+  a.grid_w = (width + tile + a.stride - 1) / a.stride + start;
+  a.pairs_w = (a.grid_w + 1) / 2;
+  a.njobs = (int64_t)a.grid_h * a.pairs_w * channels;
+  make_window(tile, a.win);
+  cudaMemsetAsync(acc, 0, (size_t)width * height * channels * sizeof(float), s);
+  count_launches(1);
+  const int sub = 32 / tile;
+  const int64_t warps_needed = (a.njobs + sub - 1) / sub;
+  int64_t ctas = (warps_needed + kWarps - 1) / kWarps;
+  const int64_t cap = (int64_t)kNumSMs * 8;  // persistent-style grid: a few CTAs per SM, each warp loops over tile pairs
+  if (ctas > cap) ctas = cap;
+  const size_t smem = (size_t)kWarps * sub * 2 * tile * (tile + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(wiener_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 32 * 33 * 4);
+    cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
+    attr = true;
+  }
+  if (tile == 32) wiener_tile_kernel<32><<<(int)ctas, kThreads, smem, s>>>(a);
+  else wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
+  return check_launch("wiener_tiles");
+}
+
+int check_args(int width, int height, int channels, int tile, int overlap) {
+  if (width <= 0 || height <= 0) { set_error("Wiener: image dimensions must be positive"); return TDB_EINVAL; }
+  if (channels != 1 && channels != 3) { set_error("input channels must be 1 or 3, got %d", channels); return TDB_EINVAL; }
+  if (tile != 16 && tile != 32) { set_error("tile_size must be 16 or 32, got %d", tile); return TDB_EINVAL; }
+  if (overlap != 2 && overlap != 4 && overlap != 8) { set_error("overlap_factor must be 2, 4, or 8"); return TDB_EINVAL; }
+  return TDB_OK;
+}
+
+}  // namespace
+}  // namespace tdb
+
+using namespace tdb;
+
+extern "C" {
+
+size_t tdb_wiener_scratch_bytes(int width, int height, int channels, int tile) {
+  (void)tile;
+  if (width <= 0 || height <= 0) return 0;
+  // accumulator (C planes interleaved) + one extra plane for the log-luminance composite
+  return ((size_t)width * height * (channels + 1)) * sizeof(float);
+}
+
+int tdb_wiener(const float *in, float *out, void *scratch, int width, int height, int channels, int tile, int overlap,
+               const float *sigmas, tdb_stream_t stream) {
+  TDB_REQUIRE(in && out && scratch && sigmas, "Wiener: null pointer");
+  if (int e = check_args(width, height, channels, tile, overlap)) return e;
+  cudaStream_t s = as_stream(stream);
+  float *acc = static_cast<float *>(scratch);
+  if (int e = run_tiles(in, acc, width, height, channels, tile, overlap, sigmas, 0.0f, s)) return e;
+  NormArgs n{};
+  n.acc = acc, n.rgb = nullptr, n.out = out, n.width = width, n.height = height, n.channels = channels, n.K = tile, n.stride = tile / overlap;
+  make_window(tile, n.win);
+  const int64_t px = (int64_t)width * height;
+  const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
+  wiener_normalize_kernel<false><<<grid, 256, 0, s>>>(n);
+  return check_launch("wiener_normalize");
+}
+
+int tdb_wiener_log_luminance(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap, float noise,
+                             float eps, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && out && scratch, "Wiener: null pointer");
+  TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
+  if (int e = check_args(width, height, 1, tile, overlap)) return e;
+  cudaStream_t s = as_stream(stream);
+  float *acc = static_cast<float *>(scratch);
+  float *lum = acc + (size_t)width * height;
+  const int64_t px = (int64_t)width * height;
+  const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
+  loglum_kernel<<<grid, 256, 0, s>>>(rgb, lum, px, eps);
+  if (int e = check_launch("wiener_log_luminance")) return e;
+  if (int e = run_tiles(lum, acc, width, height, 1, tile, overlap, nullptr, noise, s)) return e;
+  NormArgs n{};
+  n.acc = acc, n.rgb = rgb, n.out = out, n.width = width, n.height = height, n.channels = 1, n.K = tile, n.stride = tile / overlap;
+  make_window(tile, n.win);
+  wiener_normalize_kernel<true><<<grid, 256, 0, s>>>(n);
+  return check_launch("wiener_normalize");
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+"""ctypes binding of libtdb200.so (the C ABI declared in include/tdb200.h).
+
+There is no CPU fallback: if the library is missing this module raises at import, and every entry point raises
+RuntimeError when the CUDA call fails.  Build the library with `python torch-darktable_b200/build.py`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / 'lib' / 'libtdb200.so'
+
+if not _LIB_PATH.exists():
+  raise ImportError(
+    f'{_LIB_PATH} not found: the B200 CUDA library has not been built (run `python torch-darktable_b200/build.py`). '
+    'torch_darktable has no CPU fallback.'
+  )
+
+lib = C.CDLL(str(_LIB_PATH))
+
+_P, _I, _I64, _F, _U32, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32, C.c_size_t
+
+_SIGNATURES = {
+  # name: (restype, argtypes)
+  'tdb_version': (_I, []),
+  'tdb_last_error': (C.c_char_p, []),
+  'tdb_launch_count': (C.c_uint64, []),
+  'tdb_decode12_f32': (_I, [_P, _P, _I64, _I, _I, _P]),
+  'tdb_decode12_f16': (_I, [_P, _P, _I64, _I, _I, _P]),
+  'tdb_decode12_u16': (_I, [_P, _P, _I64, _I, _P]),
+  'tdb_encode12_u16': (_I, [_P, _P, _I64, _I, _P]),
+  'tdb_encode12_f32': (_I, [_P, _P, _I64, _I, _I, _P]),
+  'tdb_unpack12_wb': (_I, [_P, _P, _I, _I, _I, _U32, _F, _P, _P]),
+  'tdb_white_balance': (_I, [_P, _P, _I, _I, _U32, _P, _P]),
+  'tdb_wb_collect_samples': (_I, [_P, _I, _I, _U32, _I, _P, _P, _P, _P]),
+  'tdb_bilinear5x5': (_I, [_P, _P, _I, _I, _U32, _P]),
+  'tdb_ppg': (_I, [_P, _P, _I, _I, _U32, _F, _P]),
+  'tdb_rcd': (_I, [_P, _P, _I, _I, _U32, _P]),
+  'tdb_demosaic_packed': (_I, [_P, _P, _I, _I, _I, _U32, _I, _F, _P, _F, _P]),
+  'tdb_postprocess_scratch_bytes': (_SZ, [_I, _I]),
+  'tdb_postprocess': (_I, [_P, _P, _P, _I, _I, _U32, _I, _I, _I, _F, _P]),
+  'tdb_color_convert': (_I, [_P, _P, _I64, _I, _F, _F, _F, _P]),
+  'tdb_color_transform_3x3': (_I, [_P, _P, _I64, _P, _P]),
+  'tdb_compute_luminance': (_I, [_P, _P, _I64, _P]),
+  'tdb_compute_log_luminance': (_I, [_P, _P, _I64, _F, _P]),
+  'tdb_modify_luminance': (_I, [_P, _P, _P, _I64, _P]),
+  'tdb_modify_log_luminance': (_I, [_P, _P, _P, _I64, _F, _P]),
+  'tdb_normalize': (_I, [_P, _P, _I64, _P, _P]),
+  'tdb_bounds_init': (_I, [_P, _P]),
+  'tdb_bounds_accumulate': (_I, [_P, _I, _I, _I, _P, _P]),
+  'tdb_metrics_init': (_I, [_P, _P]),
+  'tdb_metrics_accumulate': (_I, [_P, _I, _I, _I, _F, _P, _P, _P]),
+  'tdb_metrics_finalize': (_I, [_P, _P, _P]),
+  'tdb_lerp': (_I, [_P, _P, _F, _P, _I, _P]),
+  'tdb_tonemap': (_I, [_P, _P, _I, _I, _I, _P, _F, _F, _F, _F, _P, _I, _P]),
+  'tdb_wiener_scratch_bytes': (_SZ, [_I, _I, _I, _I]),
+  'tdb_wiener': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+  'tdb_wiener_log_luminance': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _P]),
+  'tdb_bilateral_grid_size': (_I, [_I, _I, _F, _F, C.POINTER(C.c_int)]),
+  'tdb_bilateral_scratch_bytes': (_SZ, [_I, _I, _F, _F]),
+  'tdb_bilateral': (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _P]),
+  'tdb_bilateral_rgb': (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _P]),
+  'tdb_laplacian_scratch_bytes': (_SZ, [_I, _I]),
+  'tdb_laplacian': (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _F, _P]),
+}
+
+for _name, (_res, _args) in _SIGNATURES.items():
+  _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync
+  _fn.restype = _res
+  _fn.argtypes = _args
+
+EXPORTED = tuple(_SIGNATURES)
+
+
+def last_error() -> str:
+  msg = lib.tdb_last_error()
+  return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(status: int) -> None:
+  """Map a TDB_E* status to the exception type the reference raises (TORCH_CHECK -> RuntimeError)."""
+  if status != 0:
+    raise RuntimeError(last_error() or f'libtdb200 call failed with status {status}')
+
+
+def launch_count() -> int:
+  return int(lib.tdb_launch_count())

@@ -1,0 +1,203 @@
+"""ImageProcessor: packed 12-bit Bayer bytes -> display-ready uint8 RGB.
+
+Same constructor, methods, EMA state and error types as the reference's pipeline/image_processor.py:31-319, but the
+stages run as fused libtdb200 kernels on the current CUDA stream without any host synchronisation:
+
+  load_image        packed bytes -> RGB in ONE kernel (unpack + white balance + demosaic), then the post-process
+  process_rgb       normalise, Wiener on log-luminance (fused), bilateral local contrast on RGB (fused)
+  process_image_set joint bounds / metrics with device-resident EMA, tone map with the camera transform fused in
+"""
+
+from __future__ import annotations
+
+from beartype import beartype
+import torch
+
+import torch_darktable as td
+from torch_darktable.extension import extension
+
+from .camera_settings import CameraSettings
+from .config import Debayer, ImageProcessingSettings, ToneMapper
+from .transform import ImageTransform, transform
+from .util import lerp, normalize_image, resize_longest_edge
+
+
+class ImageSizeMismatchError(Exception):
+  """The byte count of a raw frame does not match the configured sensor."""
+
+  def __init__(self, message: str, image_size: tuple[int, int], packed_format: td.PackedFormat, padding: int):
+    super().__init__(message)
+    self.image_size = image_size
+    self.packed_format = packed_format
+    self.padding = padding
+
+
+_TONEMAP_OPS = {ToneMapper.reinhard: 'reinhard', ToneMapper.linear: 'linear', ToneMapper.aces: 'aces',
+                ToneMapper.adaptive_aces: 'adaptive_aces'}
+
+
+@beartype
+class ImageProcessor:
+  @beartype
+  def __init__(self, image_size: tuple[int, int], bayer_pattern: td.BayerPattern, packed_format: td.PackedFormat,
+               settings: ImageProcessingSettings, device: torch.device, white_balance: tuple[float, float, float] | None,
+               transforms: ImageTransform | dict[str, ImageTransform] = ImageTransform.none, padding: int = 0):
+    assert device.index is not None, f'Device not fully specified: {device}'
+    self.device = device
+    self.settings = settings
+    self.image_size = image_size  # (width, height)
+    self.bayer_pattern = bayer_pattern
+    self.packed_format = packed_format
+    self.transforms = transforms
+    self.padding = padding
+
+    self.metrics: torch.Tensor | None = None  # EMA state across image sets
+    self.bounds: torch.Tensor | None = None
+
+    self.white_balance = (torch.tensor(white_balance, device=device).to(torch.float32) if white_balance is not None else None)
+    self.wiener_workspace = td.Wiener(device, image_size)
+    self.rcd_workspace = td.RCD(device, image_size, bayer_pattern)
+    self._make_bilateral(settings)
+    self._make_ppg(settings)
+    self._make_postprocess(settings)
+
+  # -- workspaces -----------------------------------------------------------------------------------------------
+  def _make_bilateral(self, s: ImageProcessingSettings):
+    self.bil_workspace = td.Bilateral(self.device, self.image_size, sigma_s=s.bil_sigma_spatial, sigma_r=s.bil_sigma_luminance)
+
+  def _make_ppg(self, s: ImageProcessingSettings):
+    self.ppg_workspace = td.PPG(self.device, self.image_size, self.bayer_pattern, median_threshold=s.ppg_median_threshold)
+
+  def _make_postprocess(self, s: ImageProcessingSettings):
+    self.postprocess_workspace = td.PostProcess(self.device, self.image_size, self.bayer_pattern,
+                                                color_smoothing_passes=s.color_smoothing_passes, green_eq_local=False,
+                                                green_eq_global=True, green_eq_threshold=s.green_eq_threshold)
+
+  def update_settings(self, settings: ImageProcessingSettings):
+    old, self.settings = self.settings, settings
+
+    def changed(*names: str) -> bool:
+      return any(getattr(old, n) != getattr(settings, n) for n in names)
+
+    if changed('bil_sigma_spatial', 'enable_bilateral', 'bil_sigma_luminance'):
+      self._make_bilateral(settings)
+    if changed('ppg_median_threshold'):
+      self._make_ppg(settings)
+    if changed('color_smoothing_passes', 'green_eq_threshold'):
+      self._make_postprocess(settings)
+
+  @staticmethod
+  def from_camera_settings(camera_settings: CameraSettings, device: torch.device):
+    return ImageProcessor(camera_settings.image_size, camera_settings.bayer_pattern, camera_settings.packed_format,
+                          camera_settings.image_processing, device=device, white_balance=camera_settings.white_balance,
+                          transforms=camera_settings.transform, padding=camera_settings.padding)
+
+  def __repr__(self) -> str:
+    wb = 'None' if self.white_balance is None else '({:.3f}, {:.3f}, {:.3f})'.format(*self.white_balance.tolist())
+    if isinstance(self.transforms, ImageTransform):
+      tf = self.transforms.name
+    else:
+      tf = '{' + ', '.join(f'{k}: {v.name}' for k, v in self.transforms.items()) + '}'
+    return (f'ImageProcessor(size={self.image_size}, bayer={self.bayer_pattern.name}, format={self.packed_format.name}, '
+            f'device={self.device}, wb={wb}, padding={self.padding}, transform={tf}, debayer={self.settings.debayer.name}, '
+            f'tonemap={self.settings.tone_mapping.name})')
+
+  # -- sizes ----------------------------------------------------------------------------------------------------
+  @property
+  def final_size(self):
+    return resize_longest_edge(self.image_size, self.settings.resize_width)
+
+  @property
+  def expected_bytes(self) -> int:
+    width, height = self.image_size
+    if self.packed_format not in (td.PackedFormat.Packed12, td.PackedFormat.Packed12_IDS):
+      raise ValueError(f'Unsupported packed format: {self.packed_format}')
+    return (width * height * 3) // 2 + self.padding
+
+  def _mismatch(self, message: str) -> ImageSizeMismatchError:
+    return ImageSizeMismatchError(message, image_size=self.image_size, packed_format=self.packed_format, padding=self.padding)
+
+  def _strip(self, raw: torch.Tensor) -> torch.Tensor:
+    if raw.numel() != self.expected_bytes:
+      raise self._mismatch(f'Image size mismatch: expected {self.expected_bytes} bytes for {self.image_size} '
+                           f'{self.packed_format.name} with {self.padding} padding, got {raw.numel()} bytes. ')
+    return raw[: -self.padding] if self.padding > 0 else raw
+
+  # -- stages ---------------------------------------------------------------------------------------------------
+  @beartype
+  def load_bytes(self, bytes: torch.Tensor) -> torch.Tensor:
+    """Packed bytes -> (H, W) float32 CFA in [0, 1] (no white balance)."""
+    decoded = td.decode12(self._strip(bytes), output_dtype=torch.float32, format_type=self.packed_format)
+    width, height = self.image_size
+    if decoded.numel() != width * height:
+      raise self._mismatch(f'Decoded image size mismatch: expected {width * height} pixels ({width}x{height}), '
+                           f'got {decoded.numel()} pixels.')
+    return decoded.view(height, width)
+
+  @beartype
+  def load_image(self, bytes: torch.Tensor) -> torch.Tensor:
+    """Packed bytes -> demosaiced (and post-processed) linear RGB; one fused kernel up to the demosaic."""
+    s = self.settings
+    rgb = td.demosaic_packed(self._strip(bytes), self.image_size, self.bayer_pattern, method=s.debayer.name,
+                             format_type=self.packed_format, white_balance=self.white_balance,
+                             ppg_median_threshold=s.ppg_median_threshold)
+    return self.postprocess_workspace.process(rgb) if s.postprocess else rgb
+
+  def debayer(self, bayer_image: torch.Tensor) -> torch.Tensor:
+    """(H, W) float CFA -> RGB, stage by stage (kept for API parity; load_image uses the fused path)."""
+    assert bayer_image.ndim == 2, f'Bayer image must have 2 dimensions, got {bayer_image.shape}'
+    if self.white_balance is not None:
+      bayer_image = td.apply_white_balance(bayer_image, self.white_balance, self.bayer_pattern)
+    cfa = bayer_image.unsqueeze(-1)
+    if self.settings.debayer == Debayer.bilinear:
+      rgb = td.bilinear5x5_demosaic(cfa, self.bayer_pattern)
+    elif self.settings.debayer == Debayer.rcd:
+      rgb = self.rcd_workspace.process(cfa)
+    elif self.settings.debayer == Debayer.ppg:
+      rgb = self.ppg_workspace.process(cfa)
+    else:
+      raise AssertionError(f'Invalid debayer method: {self.settings.debayer}')
+    return self.postprocess_workspace.process(rgb) if self.settings.postprocess else rgb
+
+  @beartype
+  def process_rgb(self, rgb_raw: torch.Tensor, bounds: torch.Tensor | None = None) -> torch.Tensor:
+    if bounds is not None:
+      rgb_raw = normalize_image(rgb_raw, bounds)
+    if self.settings.enable_denoise:
+      rgb_raw = self.wiener_workspace.process_log_luminance(rgb_raw, self.settings.denoise)
+    if self.settings.enable_bilateral:
+      rgb_raw = self.bil_workspace.process_rgb(rgb_raw, self.settings.bilateral)
+    return rgb_raw
+
+  def _transform_for(self, image_name: str) -> ImageTransform:
+    return self.transforms[image_name] if isinstance(self.transforms, dict) else self.transforms
+
+  def transform(self, image: torch.Tensor, image_name: str) -> torch.Tensor:
+    return transform(image, self._transform_for(image_name))
+
+  def tonemap(self, rgb_raw: torch.Tensor, metrics: torch.Tensor | None = None,
+              image_transform: ImageTransform = ImageTransform.none) -> torch.Tensor:
+    s = self.settings
+    params = td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance)
+    if metrics is None:
+      metrics = td.compute_image_metrics([rgb_raw], stride=4, min_gray=1e-4)
+    op = _TONEMAP_OPS[s.tone_mapping]
+    return extension.tonemap(rgb_raw, op, None if op == 'aces' else metrics, params.to_cpp(), None, image_transform.name)
+
+  @beartype
+  def process(self, bytes: torch.Tensor, image_name: str) -> torch.Tensor:
+    return self.process_image_set({image_name: bytes})[image_name]
+
+  @beartype
+  def process_image_set(self, image_set_bytes: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    names = list(image_set_bytes.keys())
+    rgb_raw = [self.load_image(b) for b in image_set_bytes.values()]
+
+    bounds = td.compute_image_bounds(rgb_raw, stride=8)
+    self.bounds = lerp(self.bounds if self.bounds is not None else bounds, bounds, self.settings.moving_average)
+    rgb = [self.process_rgb(image, self.bounds) for image in rgb_raw]
+
+    metrics = td.compute_image_metrics(rgb, stride=8)
+    self.metrics = lerp(self.metrics if self.metrics is not None else metrics, metrics, self.settings.moving_average)
+
+    return {name: self.tonemap(image, self.metrics, self._transform_for(name)) for name, image in zip(names, rgb, strict=True)}
