@@ -42,6 +42,13 @@ int tdb_version(void);
 const char *tdb_last_error(void);
 /* number of kernel launches issued through this library by the calling process (for bench.py's gpu_launches) */
 uint64_t tdb_launch_count(void);
+/* Optional per-kernel timing (the counterpart of the reference's CudaTimer, csrc/cuda_utils.h:40-85).  Between
+ * tdb_timing_begin and tdb_timing_end every launch of the calling thread is followed by a cudaEventRecord on its
+ * stream; tdb_timing_end synchronises and writes "kernel_name,launches,total_ms" lines into buf (returns the number of
+ * bytes needed).  A kernel's time is the gap to the previous event on the same stream, so it is exact for launches that
+ * queue back to back on one stream.  Off by default; costs nothing when off. */
+void tdb_timing_begin(tdb_stream_t stream);
+size_t tdb_timing_end(char *buf, size_t buf_bytes);
 
 /* ---------------------------------------------------------------------------------------------------------
  * 12-bit packed codec.  Replaces decode12_float/half/u16, encode12_u16/float

@@ -190,7 +190,7 @@ int run_bilateral(const float *in, float *out, void *scratch, int width, int hei
   const size_t cells = (size_t)g.x * g.y * g.z;
   float *grid = static_cast<float *>(scratch), *blurred = grid + cells;
   cudaMemsetAsync(grid, 0, cells * sizeof(float), s);
-  count_launches(1);
+  check_launch("bilateral_zero_grid");
   // Shared-memory float atomicAdd compiles to a CAS spin loop on sm_100a (ATOMS.CAST.SPIN), so the privatised splat
   // variant is not used; red.global.add.f32 is native and the grid is L2-resident for the common sigma_s.
   dim3 sgrid(div_up(width, TP), div_up(height, TP));

@@ -24,7 +24,12 @@ void count_launches(int n);
     }                                 \
   } while (0)
 
-static inline cudaStream_t as_stream(tdb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+void note_stream(cudaStream_t s);  // remembers the stream of the entry point for the optional per-kernel timing hook
+static inline cudaStream_t as_stream(tdb_stream_t s) {
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(s);
+  note_stream(cs);
+  return cs;
+}
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- CFA helpers ------------------------------------------------------------------------------------------

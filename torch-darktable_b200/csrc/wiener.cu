@@ -306,7 +306,7 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   a.njobs = (int64_t)a.grid_h * a.pairs_w * channels;
   make_window(tile, a.win);
   cudaMemsetAsync(acc, 0, (size_t)width * height * channels * sizeof(float), s);
-  count_launches(1);
+  check_launch("wiener_zero_accumulator");
   const int sub = 32 / tile;
   const int64_t warps_needed = (a.njobs + sub - 1) / sub;
   int64_t ctas = (warps_needed + kWarps - 1) / kWarps;

@@ -26,6 +26,8 @@ _SIGNATURES = {
   'tdb_version': (_I, []),
   'tdb_last_error': (C.c_char_p, []),
   'tdb_launch_count': (C.c_uint64, []),
+  'tdb_timing_begin': (None, [_P]),
+  'tdb_timing_end': (_SZ, [C.c_char_p, _SZ]),
   'tdb_decode12_f32': (_I, [_P, _P, _I64, _I, _I, _P]),
   'tdb_decode12_f16': (_I, [_P, _P, _I64, _I, _I, _P]),
   'tdb_decode12_u16': (_I, [_P, _P, _I64, _I, _P]),
@@ -86,3 +88,18 @@ def check(status: int) -> None:
 
 def launch_count() -> int:
   return int(lib.tdb_launch_count())
+
+
+def timing_begin(stream_handle: int) -> None:
+  lib.tdb_timing_begin(C.c_void_p(stream_handle))
+
+
+def timing_end() -> dict[str, tuple[int, float]]:
+  """{kernel name: (launches, total milliseconds)} since timing_begin."""
+  buf = C.create_string_buffer(1 << 16)
+  lib.tdb_timing_end(buf, len(buf))
+  table = {}
+  for line in buf.value.decode().splitlines():
+    name, count, ms = line.rsplit(',', 2)
+    table[name] = (int(count), float(ms))
+  return table
