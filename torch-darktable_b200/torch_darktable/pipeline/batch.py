@@ -1,0 +1,57 @@
+"""Streaming frames through an ImageProcessor from HOST memory (B200 addition).
+
+The reference processes one image set at a time and synchronises the device after most ops, so host<->device copies
+never overlap its compute.  HostFrameRunner keeps three CUDA streams busy instead: while frame i is processed, frame i+1
+is copied in from pinned memory and the uint8 result of frame i-1 is copied out.  Each frame is its own image set
+(`ImageProcessor.process`), exactly what a caller of the reference does per camera frame.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from .image_processor import ImageProcessor
+
+
+class HostFrameRunner:
+  def __init__(self, processor: ImageProcessor, slots: int = 3):
+    self.processor = processor
+    self.device = processor.device
+    self.slots = slots
+    self._in = [torch.empty(processor.expected_bytes, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+    self._s_in = torch.cuda.Stream(self.device)
+    self._s_compute = torch.cuda.Stream(self.device)
+    self._s_out = torch.cuda.Stream(self.device)
+    self._copied = [torch.cuda.Event() for _ in range(slots)]
+    self._consumed = [torch.cuda.Event() for _ in range(slots)]
+    self._done = torch.cuda.Event()
+
+  def run(self, host_frames: list[torch.Tensor], host_out: list[torch.Tensor], name: str = 'cam') -> None:
+    """host_frames: pinned uint8 packed frames; host_out: pinned uint8 (H', W', 3) buffers that receive the results.
+    Returns after everything has been enqueued; call `wait()` (or synchronise the device) before reading host_out."""
+    assert len(host_frames) == len(host_out)
+    caller = torch.cuda.current_stream(self.device)
+    for s in (self._s_in, self._s_compute, self._s_out):
+      s.wait_stream(caller)
+    for i, frame in enumerate(host_frames):
+      slot = i % self.slots
+      with torch.cuda.stream(self._s_in):
+        if i >= self.slots:
+          self._s_in.wait_event(self._consumed[slot])  # the previous user of this slot has been processed
+        self._in[slot].copy_(frame, non_blocking=True)
+        self._copied[slot].record(self._s_in)
+      with torch.cuda.stream(self._s_compute):
+        self._s_compute.wait_event(self._copied[slot])
+        result = self.processor.process(self._in[slot], name)
+        self._consumed[slot].record(self._s_compute)
+        ready = torch.cuda.Event()
+        ready.record(self._s_compute)
+      with torch.cuda.stream(self._s_out):
+        self._s_out.wait_event(ready)
+        result.record_stream(self._s_out)
+        host_out[i].copy_(result, non_blocking=True)
+    self._done.record(self._s_out)
+    caller.wait_event(self._done)
+
+  def wait(self) -> None:
+    self._done.synchronize()
