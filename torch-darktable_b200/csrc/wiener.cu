@@ -17,6 +17,7 @@
 #include <cmath>
 
 #include "color_math.cuh"
+#include "fft32.cuh"
 
 namespace tdb {
 namespace {
@@ -237,6 +238,143 @@ __global__ void __launch_bounds__(kThreads) wiener_tile_kernel(const WienerArgs 
   }
 }
 
+// ---- K = 32 fast path ------------------------------------------------------------------------------------------------
+// Same warp = tile-pair organisation, rebuilt around instruction count (the v1 kernel above executed about 6400 warp
+// instructions per tile pair, half of them integer address arithmetic; ncu: profiles/r01_wiener_tile_v1_sass_hist.txt):
+//   * FMA-form DIT butterflies in both directions (fft32.cuh): natural -> bit-reversed -> natural, no reorder pass
+//   * interior tile pairs (the overwhelming majority) load and accumulate through one running pointer with
+//     immediate offsets; only border pairs take the reflecting path
+//   * transposes move (re, im) as 64-bit words: 64 + 64 shared-memory instructions instead of 128 + 128
+//   * the Hermitian pair {(ky, kx), (-ky, -kx)} shares one gain evaluation: lane ky computes both shrunk bins and
+//     hands the mirrored one to lane -ky; the 1/(2*K*K) scale is folded into the gain numerators
+template <int STRIDE>
+__global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs a) {
+  constexpr int K = 32, LD = K + 1;
+  extern __shared__ float2 s_z[];  // [kWarps][K * LD] transpose staging
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 *st = s_z + (size_t)warp * K * LD;
+  const float wc = a.win[lane];
+  const int partner = (K - lane) & (K - 1);  // lane holding -ky
+  constexpr int shift = K / STRIDE;          // the tile grid starts one tile early (denoise.cu:146)
+  const int cs = a.channels;
+  const int64_t row_step = (int64_t)a.width * cs;
+
+  const int64_t job0 = (int64_t)blockIdx.x * kWarps + warp, job_step = (int64_t)gridDim.x * kWarps;
+  for (int64_t job = job0; job < a.njobs; job += job_step) {  // whole warps: no divergence around the shuffles
+    const int ch = (int)(job % cs);
+    const int64_t t = job / cs;
+    const int px = (int)(t % a.pairs_w), gy = (int)(t / a.pairs_w);
+    const int oy = (gy - shift) * STRIDE;
+    const int ox0 = (2 * px - shift) * STRIDE, ox1 = ox0 + STRIDE;
+    const bool has_b = (2 * px + 1) < a.grid_w;
+    const bool interior = has_b && oy >= 0 && oy + K <= a.height && ox0 >= 0 && ox1 + K <= a.width;
+
+    float re[K], im[K];
+    float sum_a = 0.0f, sum_b = 0.0f;
+    if (interior) {
+      const float *p = a.in + ((int64_t)oy * a.width + ox0 + lane) * cs + ch;
+      const int boff = STRIDE * cs;
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        re[r] = __ldg(p), im[r] = __ldg(p + boff);
+        p += row_step;
+      }
+    } else {
+      const int xa = reflect_index(ox0 + lane, a.width), xb = reflect_index(ox1 + lane, a.width);
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const int64_t row = (int64_t)reflect_index(oy + r, a.height) * a.width;
+        re[r] = __ldg(a.in + (row + xa) * cs + ch);
+        im[r] = has_b ? __ldg(a.in + (row + xb) * cs + ch) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < K; r++) sum_a += re[r], sum_b += im[r];
+    const float mean_a = warp_sum(sum_a) * (1.0f / (K * K)), mean_b = warp_sum(sum_b) * (1.0f / (K * K));
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+      const float w = a.win[r] * wc;  // reference: window_fft[pos.x] * window_fft[pos.y]
+      re[r] = (re[r] - mean_a) * w, im[r] = (im[r] - mean_b) * w;
+    }
+
+    fft::fft_fwd<K>(re, im);  // along y: register p holds ky = brev(p)
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < K; p++) st[fft::brev<K>(p) * LD + lane] = make_float2(re[p], im[p]);
+    __syncwarp();
+#pragma unroll
+    for (int x = 0; x < K; x++) {
+      const float2 v = st[lane * LD + x];  // lane = ky, register = x
+      re[x] = v.x, im[x] = v.y;
+    }
+    fft::fft_fwd<K>(re, im);  // along x: register p holds kx = brev(p)
+
+    // Wiener shrinkage of the two real tiles packed as z = a + i b  (apply_gain: denoise.cu:181-185).
+    // With M = conj(Z(-k)):  A = (Z + M)/2, iB = (Z - M)/2, |A|^2 = (sr^2 + di^2)/4, |B|^2 = (si^2 + dr^2)/4 where
+    // s = Z + Z(-k), d = Z - Z(-k) componentwise; shrunk Z' = gA A + i gB B.  Scale kq = 1/(2 K^2) folded in.
+    {
+      const float sg = a.sigmas ? __ldg(a.sigmas + ch) : a.sigma_value;
+      constexpr float kq = 1.0f / (2.0f * K * K);
+      const float n0 = kq * (kEps - sg * sg);
+#pragma unroll
+      for (int p = 0; p < K; p++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int q = fft::brev<K>((K - fft::brev<K>(p)) & (K - 1));  // register holding -kx
+        if (q < p) continue;                                           // written by the exchange below
+        const float zr = re[p], zi = im[p];
+        const float mr = __shfl_sync(0xffffffffu, re[q], partner), mi = __shfl_sync(0xffffffffu, im[q], partner);
+        const float sr = zr + mr, dr = zr - mr, si = zi + mi, di = zi - mi;
+        const float qa = fmaf(sr, sr, di * di), qb = fmaf(si, si, dr * dr);
+        const float ga = __fdividef(fmaxf(fmaf(qa, 0.25f * kq, n0), 0.0f), fmaf(qa, 0.25f, kEps));
+        const float gb = __fdividef(fmaxf(fmaf(qb, 0.25f * kq, n0), 0.0f), fmaf(qb, 0.25f, kEps));
+        const float t0 = ga * sr, t1 = gb * dr, t2 = ga * di, t3 = gb * si;
+        re[p] = t0 + t1, im[p] = t2 + t3;
+        if (q != p) {  // the mirrored bin (-ky, -kx) lives in the partner lane's register q
+          re[q] = __shfl_sync(0xffffffffu, t0 - t1, partner);
+          im[q] = __shfl_sync(0xffffffffu, t3 - t2, partner);
+        }
+      }
+    }
+
+    fft::fft_inv<K>(re, im);  // along x: register = x
+    __syncwarp();
+#pragma unroll
+    for (int x = 0; x < K; x++) st[lane * LD + x] = make_float2(re[x], im[x]);
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < K; p++) {
+      const float2 v = st[fft::brev<K>(p) * LD + lane];  // lane = x, register p holds ky = brev(p)
+      re[p] = v.x, im[p] = v.y;
+    }
+    fft::fft_inv<K>(re, im);  // along y: register = row
+
+    // overlap-add: (value + mean * w_fft) * w_interp   (store_pixel, denoise.cu:150-178)
+    if (interior) {
+      float *o = a.acc + ((int64_t)oy * a.width + ox0 + lane) * cs + ch;
+      const int boff = STRIDE * cs;
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const float w = a.win[r] * wc;
+        atomicAdd(o, fmaf(mean_a, w, re[r]) * w);
+        atomicAdd(o + boff, fmaf(mean_b, w, im[r]) * w);
+        o += row_step;
+      }
+    } else {
+      const int xa = ox0 + lane, xb = ox1 + lane;
+      const bool in_a = xa >= 0 && xa < a.width, in_b = has_b && xb >= 0 && xb < a.width;
+#pragma unroll
+      for (int r = 0; r < K; r++) {
+        const int y = oy + r;
+        if (y < 0 || y >= a.height) continue;
+        const float w = a.win[r] * wc;
+        if (in_a) atomicAdd(a.acc + ((int64_t)y * a.width + xa) * cs + ch, fmaf(mean_a, w, re[r]) * w);
+        if (in_b) atomicAdd(a.acc + ((int64_t)y * a.width + xb) * cs + ch, fmaf(mean_b, w, im[r]) * w);
+      }
+    }
+  }
+}
+
 // closed-form weight mask: sum over the overlap^2 covering tiles of (w_fft * w_interp)(x) * (w_fft * w_interp)(y)
 struct NormArgs {
   const float *acc;
@@ -315,12 +453,27 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   const size_t smem = (size_t)kWarps * sub * 2 * tile * (tile + 1) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(wiener_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 32 * 33 * 4);
     cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
     attr = true;
   }
-  if (tile == 32) wiener_tile_kernel<32><<<(int)ctas, kThreads, smem, s>>>(a);
-  else wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
+  if (tile == 32) {
+    const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
+    static bool attr32 = false;
+    if (!attr32) {
+      cudaFuncSetAttribute(wiener32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      attr32 = true;
+    }
+    // persistent grid: two CTAs per SM, every warp walks tile pairs that are neighbours in x (shared lines in L1)
+    int64_t ctas32 = (a.njobs + kWarps - 1) / kWarps;
+    if (ctas32 > 2 * kNumSMs) ctas32 = 2 * kNumSMs;
+    if (a.stride == 8) wiener32_kernel<8><<<(int)ctas32, kThreads, smem32, s>>>(a);
+    else if (a.stride == 4) wiener32_kernel<4><<<(int)ctas32, kThreads, smem32, s>>>(a);
+    else wiener32_kernel<16><<<(int)ctas32, kThreads, smem32, s>>>(a);
+  } else {
+    wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
+  }
   return check_launch("wiener_tiles");
 }
 
