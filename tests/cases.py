@@ -14,15 +14,34 @@ from pathlib import Path
 import numpy as np
 
 GOLDEN_DIR = Path(__file__).resolve().parent / 'golden'
-GROUPS = ('packed', 'demosaic', 'color', 'filters', 'pipeline')
+GROUPS = ('packed', 'demosaic', 'color', 'filters', 'pipeline', 'mid')
+
+
+def synth_inputs(recipe: dict) -> dict:
+  """Inputs of the 'mid' golden cases are regenerated from tests/synth.py instead of being stored."""
+  import synth
+  h, w = recipe['h'], recipe['w']
+  if recipe['kind'] == 'cfa':
+    return {'cfa': synth.mosaic(synth.scene_rgb(h, w, recipe['seed']), recipe['pattern'])}
+  if recipe['kind'] == 'noisy_rgb':
+    noise = np.random.default_rng(recipe['noise_seed']).normal(0, recipe['noise'], size=(h, w, 3))
+    return {'x': np.clip(synth.scene_rgb(h, w, recipe['seed']) + noise, 0, 1).astype(np.float32)}
+  return {'x': synth.scene_rgb(h, w, recipe['seed'])}
 
 
 def load_group(group: str):
-  z = np.load(GOLDEN_DIR / f'{group}.npz')
+  path = GOLDEN_DIR / f'{group}.npz'
+  if not path.exists():
+    return []
+  z = np.load(path)
   manifest = json.loads(str(z['manifest']))
   cases = []
   for name, info in manifest.items():
     ins = {k.split('/in/')[1]: z[k] for k in z.files if k.startswith(f'{name}/in/')}
+    if 'synth' in info['params']:
+      info['params'] = dict(info['params'])
+      recipe = dict(info['params'].pop('synth'), pattern=info['params'].get('pattern'))
+      ins = synth_inputs(recipe)
     outs = {k.split('/out/')[1]: z[k] for k in z.files if k.startswith(f'{name}/out/')}
     cases.append((name, info['op'], info['params'], ins, outs))
   return cases
@@ -69,10 +88,21 @@ def compare(op: str, got: np.ndarray, ref: np.ndarray, tol=None) -> str | None:
     same = np.array_equal(got.view(np.uint8) if got.dtype.kind == 'f' else got,
                           ref.view(np.uint8) if ref.dtype.kind == 'f' else ref)
     return None if same else f'not bit-exact: {np.sum(got != ref)} of {ref.size} differ'
+  if isinstance(tol, tuple) and tol[0] == 'outliers':
+    _, t, frac, hard = tol
+    d = np.nan_to_num(np.abs(got.astype(np.float64) - ref.astype(np.float64)), nan=np.inf)
+    if d.max() > hard:
+      return f'max abs diff {d.max():.3e} > hard limit {hard:g}'
+    if (d > t).mean() > frac:
+      return f'fraction beyond {t:g}: {(d > t).mean():.2e} > {frac:g}'
+    return None
   if isinstance(tol, tuple):
-    _, frac = tol
+    frac = tol[1]
     d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
-    if d.max() > 1:
+    if len(tol) > 2:  # ('u8', frac, outlier_frac): a few samples may be further than 1 LSB apart
+      if (d > 1).mean() > tol[2]:
+        return f'uint8 fraction beyond 1 LSB {(d > 1).mean():.2e} > {tol[2]}'
+    elif d.max() > 1:
       return f'uint8 max diff {d.max()} > 1 LSB'
     if (d > 0).mean() > frac:
       return f'uint8 fraction different {(d > 0).mean():.2e} > {frac}'
@@ -196,8 +226,16 @@ class OracleImpl:
 
 PIPELINE_STATE_TOL = 2e-6  # bounds/metrics vectors inside the pipeline cases
 
+# Comparisons that involve the CPU ORACLE on frames of more than a few tiles.  RCD picks between two interpolation
+# directions with `|0.5 - c0| < |0.5 - nb| ? nb : c0` (reference rcd.cu:117-121) where c0/nb come out of approximate
+# (--use_fast_math) divisions.  The oracle is IEEE C, so on ~2e-4 of the pixels the select flips and those pixels differ by
+# up to ~2e-2 (measured against the reference itself: tools/three_way.py, profiles/r01_three_way_mid.log) while the CUDA
+# path, compiled like the reference, stays within 2.4e-7 of it everywhere.  Against the reference's golden outputs the CUDA
+# path is held to the strict TOLERANCE table; only oracle comparisons get the outlier allowance.
+ORACLE_TOLERANCE = {'rcd': ('outliers', 5e-6, 5e-4, 0.05), 'pipeline': ('u8', 1e-3, 2e-4)}
 
-def check_outputs(op: str, got: dict, ref: dict) -> list[str]:
+
+def check_outputs(op: str, got: dict, ref: dict, oracle: bool = False) -> list[str]:
   problems = []
   for key, r in ref.items():
     if key not in got:
@@ -205,6 +243,8 @@ def check_outputs(op: str, got: dict, ref: dict) -> list[str]:
       continue
     if op == 'pipeline' and key.startswith(('bounds', 'metrics')):
       msg = compare(op, got[key], r, PIPELINE_STATE_TOL)
+    elif oracle and op in ORACLE_TOLERANCE:
+      msg = compare(op, got[key], r, ORACLE_TOLERANCE[op])
     else:
       msg = compare(op, got[key], r)
     if msg:

@@ -316,6 +316,26 @@ def pipeline_cases(b: Book):
           {'frame0': frames[0], 'frame1': frames[1], 'frame2': frames[2]}, outs)
 
 
+def mid_cases(b: Book):
+  """Frames that span many CTA tiles of the new kernels (the other groups are 64x96): multi-tile RCD for two patterns,
+  the Wiener log-luminance composite and the bilateral composite.  Inputs are NOT stored (they are regenerated from
+  tests/synth.py by seed) to keep the fixture small; the manifest carries the recipe."""
+  h, w = 130, 372
+  for pattern in ('RGGB', 'GBRG'):
+    cfa = synth.mosaic(synth.scene_rgb(h, w, 7), pattern)
+    out = td.RCD(dev, (w, h), td.BayerPattern[pattern]).process(cuda(cfa).unsqueeze(-1)).clone()
+    b.add(f'rcd_mid_{pattern}', 'rcd', {'pattern': pattern, 'synth': {'kind': 'cfa', 'h': h, 'w': w, 'seed': 7}}, {}, {'out': out})
+  h, w = 130, 204
+  x = np.clip(synth.scene_rgb(h, w, 17) + np.random.default_rng(6).normal(0, 0.02, size=(h, w, 3)), 0, 1).astype(np.float32)
+  out = td.Wiener(dev, (w, h)).process_log_luminance(cuda(x), 0.075, 1e-4)
+  b.add('wiener_log_luminance_mid', 'wiener_log_luminance', {'noise': 0.075, 'eps': 1e-4,
+        'synth': {'kind': 'noisy_rgb', 'h': h, 'w': w, 'seed': 17, 'noise_seed': 6, 'noise': 0.02}}, {}, {'out': out})
+  x = synth.scene_rgb(h, w, 19)
+  out = td.Bilateral(dev, (w, h), sigma_s=2.0, sigma_r=0.2).process_rgb(cuda(x), 0.4)
+  b.add('bilateral_rgb_mid', 'bilateral_rgb', {'sigma_s': 2.0, 'sigma_r': 0.2, 'detail': 0.4,
+        'synth': {'kind': 'rgb', 'h': h, 'w': w, 'seed': 19}}, {}, {'out': out})
+
+
 def main():
   out_dir = Path(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/golden')
   out_dir.mkdir(parents=True, exist_ok=True)
@@ -326,6 +346,7 @@ def main():
     'color': [color_cases, tonemap_cases],
     'filters': [wiener_cases, local_contrast_cases],
     'pipeline': [pipeline_cases],
+    'mid': [mid_cases],
   }
   only = sys.argv[2].split(',') if len(sys.argv) > 2 else list(groups)
   errors = []

@@ -1,0 +1,99 @@
+"""GPU parity, part 2: the CUDA path against the CPU oracle at sizes that span many CTA tiles.
+
+The golden vectors of the reference (tests/golden) are 64x96 frames, i.e. a handful of tiles per kernel.  The kernels are
+tiled (32x32, 56x32, 64x64 pixel tiles, 8-pixel Wiener strides, ...), so every stage is run here on seeded synthetic
+frames whose sides are NOT multiples of the tile sizes, with widths both divisible by four (128-bit paths) and not
+(scalar fallbacks), and compared with the oracle under the per-op tolerances of tests/cases.py.
+"""
+
+import numpy as np
+import pytest
+
+import cases
+import synth
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(250, 372), (130, 202), (516, 1100)]  # (H, W): multi-tile + ragged, width % 4 != 0, larger
+
+
+@pytest.fixture(scope='module')
+def impl():
+  import torch
+  assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+  from cuda_impl import CudaImpl
+  return CudaImpl()
+
+
+@pytest.fixture(scope='module')
+def oracle():
+  return cases.OracleImpl()
+
+
+def check(op, impl, oracle, params, ins):
+  got = cases.run_case(impl, op, params, ins)
+  want = cases.run_case(oracle, op, params, ins)
+  problems = cases.check_outputs(op, got, want, oracle=True)
+  assert not problems, f'{op} {params}: ' + '; '.join(problems)
+
+
+def cfa_of(h, w, pattern, seed):
+  return synth.mosaic(synth.scene_rgb(h, w, seed), pattern)
+
+
+@pytest.mark.parametrize('h,w', SIZES)
+@pytest.mark.parametrize('pattern', ['RGGB', 'GBRG'])
+@pytest.mark.parametrize('op', ['rcd', 'ppg', 'bilinear5x5_demosaic'])
+def test_demosaic(impl, oracle, op, pattern, h, w):
+  h, w = h & ~1, w & ~1
+  params = {'pattern': pattern}
+  if op == 'ppg':
+    params['median_threshold'] = 0.0
+  check(op, impl, oracle, params, {'cfa': cfa_of(h, w, pattern, 7)})
+
+
+@pytest.mark.parametrize('h,w', SIZES)
+@pytest.mark.parametrize('passes,glob,loc', [(1, False, False), (3, True, False), (4, True, True), (5, False, False), (9, True, False),
+                                             (0, True, True)])
+def test_postprocess(impl, oracle, passes, glob, loc, h, w):
+  rng = np.random.default_rng(3)
+  rgb = synth.scene_rgb(h, w, 11) + rng.normal(0, 0.02, size=(h, w, 3)).astype(np.float32)  # some negatives: the clamps matter
+  rgb[0::2, 1::2, 1] *= 1.04
+  params = {'pattern': 'RGGB', 'color_smoothing_passes': passes, 'green_eq_local': loc, 'green_eq_global': glob,
+            'green_eq_threshold': 4.0}
+  check('postprocess', impl, oracle, params, {'rgb': rgb.astype(np.float32)})
+
+
+@pytest.mark.parametrize('h,w', SIZES[:2])
+@pytest.mark.parametrize('k,ov,c', [(32, 4, 1), (32, 4, 3), (32, 2, 1), (32, 8, 1), (16, 4, 1)])
+def test_wiener(impl, oracle, k, ov, c, h, w):
+  rng = np.random.default_rng(5)
+  x = (synth.scene_rgb(h, w, 13)[..., :c] + rng.normal(0, 0.03, size=(h, w, c))).astype(np.float32)
+  sigmas = [0.03, 0.05, 0.02][:c]
+  check('wiener', impl, oracle, {'sigmas': sigmas, 'tile_size': k, 'overlap_factor': ov}, {'x': x})
+
+
+@pytest.mark.parametrize('h,w', SIZES)
+def test_wiener_log_luminance(impl, oracle, h, w):
+  rng = np.random.default_rng(6)
+  x = np.clip(synth.scene_rgb(h, w, 17) + rng.normal(0, 0.02, size=(h, w, 3)), 0, 1).astype(np.float32)
+  check('wiener_log_luminance', impl, oracle, {'noise': 0.075, 'eps': 1e-4}, {'x': x})
+
+
+@pytest.mark.parametrize('h,w', SIZES)
+@pytest.mark.parametrize('ss,sr', [(2.0, 0.2), (8.0, 0.1)])
+def test_bilateral(impl, oracle, ss, sr, h, w):
+  x = synth.scene_rgb(h, w, 19)
+  check('bilateral_rgb', impl, oracle, {'sigma_s': ss, 'sigma_r': sr, 'detail': 0.4}, {'x': x})
+  check('bilateral', impl, oracle, {'sigma_s': ss, 'sigma_r': sr, 'detail': 0.2}, {'lum': np.ascontiguousarray(x[..., 1])})
+
+
+@pytest.mark.parametrize('h,w', [(250, 372), (130, 204)])
+@pytest.mark.parametrize('tm,deb,tf', [('adaptive_aces', 'rcd', 'rotate_270'), ('reinhard', 'ppg', 'rotate_90'),
+                                       ('aces', 'bilinear', 'transpose'), ('linear', 'rcd', 'rotate_180'),
+                                       ('adaptive_aces', 'rcd', 'flip_vert')])
+def test_pipeline(impl, oracle, tm, deb, tf, h, w):
+  frames = [synth.packed_frame(h, w, seed=40 + i) for i in range(3)]
+  params = {'width': w, 'height': h, 'white_balance': [1.8, 1.0, 2.1], 'debayer': deb, 'tone_mapping': tm,
+            'moving_average': 0.5, 'transform': tf}
+  check('pipeline', impl, oracle, params, {'frame0': frames[0], 'frame1': frames[1], 'frame2': frames[2]})

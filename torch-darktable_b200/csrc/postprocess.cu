@@ -5,32 +5,13 @@
 // middle of the stream.  Here all smoothing passes run inside one shared-memory tile (halo = number of passes), the
 // green sums are taken in the same kernel (smoothing never changes G apart from the >= 0 clamp), the ratio stays on the
 // device, and one second kernel applies the global ratio and the local equilibration: 24 B/px per kernel, no sync.
-#include "tdb_common.cuh"
+#include "cfa_tile.cuh"
 
 namespace tdb {
 namespace {
 
 constexpr int T = 32;
 constexpr int kThreads = 256;
-constexpr int kMaxFusedPasses = 6;
-
-__device__ __forceinline__ void cas(float &a, float &b) {
-  const float x = a;
-  const bool c = a > b;
-  a = c ? b : a;
-  b = c ? x : b;
-}
-// same exchange sequence as the reference's 19-exchange network (csrc/reduction.h:93-116)
-__device__ __forceinline__ float median9(float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7, float s8) {
-  cas(s1, s2); cas(s4, s5); cas(s7, s8);
-  cas(s0, s1); cas(s3, s4); cas(s6, s7);
-  cas(s1, s2); cas(s4, s5); cas(s7, s8);
-  cas(s0, s3); cas(s5, s8); cas(s4, s7);
-  cas(s3, s6); cas(s1, s4); cas(s2, s5);
-  cas(s4, s7); cas(s4, s2); cas(s6, s4);
-  cas(s4, s2);
-  return s4;
-}
 
 struct Header {          // first bytes of the scratch buffer
   float sum1, sum2;      // G1 / G2 sums
@@ -38,75 +19,136 @@ struct Header {          // first bytes of the scratch buffer
   float pad;
 };
 
-// smoothing passes + (optionally) per-CTA green sums of the result
+// ---- colour smoothing ------------------------------------------------------------------------------------------------
+// v1 of this kernel ran the reference's 19-exchange network twice per pixel per pass on interleaved RGB in shared memory
+// and was bound by the ALU pipe (FMNMX) and by index arithmetic (ncu: 830 thread instructions per output pixel).  Here:
+//   * the tile lives as planes: G and the two colour differences R-G, B-G (ping-pong), so a pass reads 2 x 9 floats
+//     instead of 27 and writes the differences the next pass needs
+//   * a thread owns one column and walks down its row segment; each row contributes one SORTED horizontal triple per
+//     channel (3 exchanges) that three consecutive outputs share, and the median of nine is
+//     med3(max of the three lows, med3 of the three mids, min of the three highs) with FMNMX3 for the 3-input min/max:
+//     16 min/max per channel per output instead of 38.  The median VALUE is the same as the reference network's.
+//   * tile 56 x 32 outputs inside a 64-column patch: lanes map to consecutive columns (conflict-free planes), the patch
+//     is staged and the result written with 128-bit accesses.
+constexpr int SW = 56, SH = 32;      // output tile
+constexpr int SHX = 4;               // x halo (keeps every patch row 16-byte aligned in global memory)
+constexpr int SPW = SW + 2 * SHX;    // 64 patch columns
+constexpr int kMaxFusedPasses = 4;   // <= SHX
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float med3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
+struct Triple {
+  float lo, mid, hi;
+};
+__device__ __forceinline__ Triple sort3(float a, float b, float c) {
+  const float t1 = fminf(a, b), t2 = fmaxf(a, b);
+  return Triple{fminf(t1, c), fmaxf(t1, fminf(t2, c)), fmaxf(t2, c)};
+}
+__device__ __forceinline__ float median_of_rows(const Triple &a, const Triple &b, const Triple &c) {
+  return med3(max3(a.lo, b.lo, c.lo), med3(a.mid, b.mid, c.mid), min3(a.hi, b.hi, c.hi));
+}
+
+// 1..kMaxFusedPasses smoothing passes (+ per-CTA green sums of the result)
 __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height,
-                                                          uint32_t filters, int passes, int want_sums, int clamp_sums,
-                                                          float *__restrict__ partials) {
+                                                          uint32_t filters, int passes, int want_sums, float *__restrict__ partials) {
   extern __shared__ __align__(16) float sm[];
-  const int halo = passes;
-  const int PW = T + 2 * halo;
-  float *buf0 = sm, *buf1 = sm + PW * PW * 3;
+  const int PH = SH + 2 * passes;     // patch rows
+  const int plane = PH * SPW;
+  // plane order: D0r D0b X D1r D1b G.  {X, D1r, D1b} stages the raw RGB patch; the output tile takes whichever
+  // three contiguous planes the last pass does not read
+  float *d0 = sm, *xpl = sm + 2 * plane, *d1 = sm + 3 * plane, *gpl = sm + 5 * plane;
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
-  // stage: zero outside the image (postprocess.cu:58-59)
-  for (int i = tid; i < PW * PW; i += kThreads) {
-    const int ly = i / PW, lx = i - ly * PW;
-    const int x = x0 - halo + lx, y = y0 - halo + ly;
-    float r = 0.0f, g = 0.0f, b = 0.0f;
-    if (x >= 0 && y >= 0 && x < width && y < height) {
-      const float *p = in + 3 * ((int64_t)y * width + x);
-      r = __ldg(p), g = __ldg(p + 1), b = __ldg(p + 2);
+  const int x0 = blockIdx.x * SW, y0 = blockIdx.y * SH;
+  const int gx0 = x0 - SHX, gy0 = y0 - passes;  // image coordinates of patch cell (0, 0)
+
+  // ---- stage the raw patch (zero outside the image, postprocess.cu:58-59)
+  float *raw = xpl;  // [PH][SPW * 3]
+  const bool vec = ((width & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  if (vec) {
+    constexpr int QR = SPW * 3 / 4;  // float4 per patch row
+    for (int i = tid; i < PH * QR; i += kThreads) {
+      const int ly = i / QR, q = i - ly * QR;
+      const int y = gy0 + ly, x = gx0 + (4 * q) / 3;  // first pixel touched; a float4 never straddles the image edge
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (y >= 0 && y < height && x >= 0 && x < width) v = ld_stream(reinterpret_cast<const float4 *>(in + 3 * ((int64_t)y * width + gx0)) + q);
+      *reinterpret_cast<float4 *>(raw + ly * SPW * 3 + 4 * q) = v;
     }
-    buf0[3 * i] = r, buf0[3 * i + 1] = g, buf0[3 * i + 2] = b;
+  } else {
+    for (int i = tid; i < PH * SPW * 3; i += kThreads) {
+      const int ly = i / (SPW * 3), f = i - ly * (SPW * 3);
+      const int y = gy0 + ly, x = gx0 + f / 3;
+      raw[i] = (y >= 0 && y < height && x >= 0 && x < width) ? __ldg(in + 3 * ((int64_t)y * width + gx0) + f) : 0.0f;
+    }
   }
   __syncthreads();
-  float *src = buf0, *dst = buf1;
-  for (int pass = 0; pass < passes; pass++) {
-    const int m = pass + 1;  // the valid region shrinks by one ring per pass
-    const int N = PW - 2 * m;
-    for (int i = tid; i < N * N; i += kThreads) {
-      const int ly = m + i / N, lx = m + i % N;
-      const int x = x0 - halo + lx, y = y0 - halo + ly;
-      float r = 0.0f, g = 0.0f, b = 0.0f;
-      if (x >= 0 && y >= 0 && x < width && y < height) {  // outside stays zero for the next pass
-        const float *c = src + 3 * (ly * PW + lx);
-        const int R = 3 * PW;
-#define DR(o) (c[(o)] - c[(o) + 1])
-#define DB(o) (c[(o) + 2] - c[(o) + 1])
-        const float mr = median9(DR(-R - 3), DR(-R), DR(-R + 3), DR(-3), DR(0), DR(3), DR(R - 3), DR(R), DR(R + 3));
-        const float mb = median9(DB(-R - 3), DB(-R), DB(-R + 3), DB(-3), DB(0), DB(3), DB(R - 3), DB(R), DB(R + 3));
-#undef DR
-#undef DB
-        g = c[1];
-        r = fmaxf(mr + g, 0.0f), b = fmaxf(mb + g, 0.0f), g = fmaxf(g, 0.0f);
-      }
-      float *d = dst + 3 * (ly * PW + lx);
-      d[0] = r, d[1] = g, d[2] = b;
-    }
-    __syncthreads();
-    float *t = src; src = dst; dst = t;
+  for (int i = tid; i < PH * SPW; i += kThreads) {
+    const float r = raw[3 * i], g = raw[3 * i + 1], b = raw[3 * i + 2];
+    gpl[i] = g, d0[i] = r - g, d0[plane + i] = b - g;
   }
-  // write the tile + green sums over the even-cropped image (postprocess.cu:195-203)
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int cg = warp & 1, sg = warp >> 1;  // column group (2 x 32 lanes), row segment (4)
+  float *outt = (passes & 1) ? xpl : d0;    // the last pass reads D[(passes-1)&1]; the tile takes the other three planes
   float s1 = 0.0f, s2 = 0.0f;
   const int we = width & ~1, he = height & ~1;
-  for (int i = tid; i < T * T; i += kThreads) {
-    const int ly = i / T, lx = i - ly * T;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= width || y >= height) continue;
-    const float *c = src + 3 * ((ly + halo) * PW + lx + halo);
-    if (want_sums && x < we && y < he && fc(y & 1, x & 1, filters) == 1) {
-      const float g = clamp_sums ? fmaxf(c[1], 0.0f) : c[1];
-      if (y & 1) s2 += g; else s1 += g;
+  for (int m = 1; m <= passes; m++) {
+    const float *src = ((m - 1) & 1) ? d1 : d0;
+    float *dst = (m & 1) ? d1 : d0;
+    const bool last = m == passes;
+    const int grow = passes - m;  // how far beyond the output tile this pass must still be valid
+    const int r_lo = passes - grow, r_hi = passes + SH + grow;  // rows [r_lo, r_hi)
+    const int c_lo = SHX - grow, c_hi = SHX + SW + grow;
+    const int seg = (r_hi - r_lo + 3) >> 2;
+    const int rb = r_lo + sg * seg, re = min(rb + seg, r_hi);
+    const int col = c_lo + cg * 32 + lane;
+    if (col < c_hi && rb < re) {
+      const int gx = gx0 + col;
+      const bool col_in = gx >= 0 && gx < width;
+      const float *pr = src + (rb - 1) * SPW + col, *pb = pr + plane;
+      Triple ra = sort3(pr[-1], pr[0], pr[1]), ba = sort3(pb[-1], pb[0], pb[1]);
+      pr += SPW, pb += SPW;
+      Triple rbt = sort3(pr[-1], pr[0], pr[1]), bbt = sort3(pb[-1], pb[0], pb[1]);
+      for (int r = rb; r < re; r++) {
+        pr += SPW, pb += SPW;
+        const Triple rc = sort3(pr[-1], pr[0], pr[1]), bc = sort3(pb[-1], pb[0], pb[1]);
+        const int gy = gy0 + r;
+        float R = 0.0f, G = 0.0f, B = 0.0f;
+        if (col_in && gy >= 0 && gy < height) {  // outside stays zero for the next pass
+          const float mr = median_of_rows(ra, rbt, rc), mb = median_of_rows(ba, bbt, bc);
+          const float g = gpl[r * SPW + col];
+          R = fmaxf(mr + g, 0.0f), B = fmaxf(mb + g, 0.0f), G = fmaxf(g, 0.0f);
+        }
+        if (!last) {
+          dst[r * SPW + col] = R - G, dst[plane + r * SPW + col] = B - G;
+          gpl[r * SPW + col] = G;
+        } else {
+          float *o = outt + 3 * ((r - passes) * SW + (col - SHX));
+          o[0] = R, o[1] = G, o[2] = B;
+          // green sums over the even-cropped image (postprocess.cu:195-203)
+          if (want_sums && gx < we && gy < he && col_in && gy >= 0 && fc(gy & 1, gx & 1, filters) == 1) {
+            if (gy & 1) s2 += G; else s1 += G;
+          }
+        }
+        ra = rbt, rbt = rc, ba = bbt, bbt = bc;
+      }
     }
-    if (out) {
-      float *o = out + 3 * ((int64_t)y * width + x);
-      o[0] = c[0], o[1] = c[1], o[2] = c[2];
-    }
+    __syncthreads();
   }
+  store_rgb_tile(outt, SW * 3, out, x0, y0, SW, SH, width, height);
   if (want_sums) {
     __shared__ float red[2][kThreads / 32];
     s1 = warp_sum(s1), s2 = warp_sum(s2);
-    if ((tid & 31) == 0) red[0][tid >> 5] = s1, red[1][tid >> 5] = s2;
+    if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
     __syncthreads();
     if (tid == 0) {
       float a = 0.0f, b = 0.0f;
@@ -115,6 +157,33 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
       const int blk = blockIdx.y * gridDim.x + blockIdx.x;
       partials[2 * blk] = a, partials[2 * blk + 1] = b;
     }
+  }
+}
+
+// green sums of an image that is not smoothed (passes == 0): one CTA per 32 x 32 tile
+__global__ void __launch_bounds__(kThreads) green_sums_kernel(const float *__restrict__ in, int width, int height, uint32_t filters,
+                                                              float *__restrict__ partials) {
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+  float s1 = 0.0f, s2 = 0.0f;
+  const int we = width & ~1, he = height & ~1;
+  for (int i = tid; i < T * T; i += kThreads) {
+    const int x = x0 + (i & (T - 1)), y = y0 + i / T;
+    if (x < we && y < he && fc(y & 1, x & 1, filters) == 1) {
+      const float g = __ldg(in + 3 * ((int64_t)y * width + x) + 1);
+      if (y & 1) s2 += g; else s1 += g;
+    }
+  }
+  __shared__ float red[2][kThreads / 32];
+  s1 = warp_sum(s1), s2 = warp_sum(s2);
+  if ((tid & 31) == 0) red[0][tid >> 5] = s1, red[1][tid >> 5] = s2;
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) a += red[0][w], b += red[1][w];
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    partials[2 * blk] = a, partials[2 * blk + 1] = b;
   }
 }
 
@@ -219,30 +288,33 @@ int tdb_postprocess(const float *in, float *out, void *scratch, int width, int h
 
   static bool attr = false;
   if (!attr) {
-    const int pw = T + 2 * kMaxFusedPasses;
-    cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * pw * pw * 3 * sizeof(float)));
+    cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(6 * (SH + 2 * kMaxFusedPasses) * SPW * sizeof(float)));
     attr = true;
   }
   const float *cur = in;
   int remaining = passes;
-  bool sums_done = false;
+  size_t npartials = nblk;
   // all passes fused in one launch when they fit (the pipeline default is 3); longer chains go in chunks
-  while (remaining > 0 || (green_eq_global && !sums_done)) {
+  while (remaining > 0) {
     const int chunk = remaining < kMaxFusedPasses ? remaining : kMaxFusedPasses;
     const bool last = (remaining - chunk) == 0;
-    float *dst = nullptr;
-    if (chunk > 0) dst = (last && !eq) ? out : (cur == img_a ? img_b : img_a);
+    float *dst = (last && !eq) ? out : (cur == img_a ? img_b : img_a);
     const int want_sums = last && green_eq_global;
-    const int pw = T + 2 * chunk;
-    smooth_kernel<<<grid, kThreads, 2 * pw * pw * 3 * sizeof(float), s>>>(cur, dst, width, height, filters, chunk, want_sums,
-                                                                          passes > 0, partials);
+    dim3 sgrid(div_up(width, SW), div_up(height, SH));
+    smooth_kernel<<<sgrid, kThreads, 6 * (SH + 2 * chunk) * SPW * sizeof(float), s>>>(cur, dst, width, height, filters, chunk, want_sums,
+                                                                                      partials);
     if (int e = check_launch("color_smoothing")) return e;
-    if (dst) cur = dst;
+    if (want_sums) npartials = (size_t)sgrid.x * sgrid.y;
+    cur = dst;
     remaining -= chunk;
-    if (want_sums) sums_done = true;
+  }
+  if (green_eq_global && passes == 0) {
+    green_sums_kernel<<<grid, kThreads, 0, s>>>(cur, width, height, filters, partials);
+    if (int e = check_launch("green_sums")) return e;
   }
   if (green_eq_global) {
-    ratio_kernel<<<1, 1024, 0, s>>>(partials, (int)nblk, hdr);
+    ratio_kernel<<<1, 1024, 0, s>>>(partials, (int)npartials, hdr);
     if (int e = check_launch("green_eq_ratio")) return e;
   }
   if (eq) {
