@@ -36,7 +36,8 @@ __device__ __forceinline__ float finish_sample(const CfaSource &s, uint32_t raw,
   float v = (float)raw * (1.0f / 4095.0f);
   if (s.apply) {
     v -= s.black;
-    if (s.apply == 2) v = clip01(v * s.gain[y & 1][x & 1]);
+    // selects on compile-time indices: a dynamically indexed member would push the whole struct into local memory
+    if (s.apply == 2) v = clip01(v * ((y & 1) ? ((x & 1) ? s.gain[1][1] : s.gain[1][0]) : ((x & 1) ? s.gain[0][1] : s.gain[0][0])));
   }
   return v;
 }
