@@ -89,14 +89,19 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const float *__restrict
       ox = 1, oy = g.x, oz = g.x * g.y;
       base = grid + s.ix + (int64_t)g.x * (s.iy + (int64_t)g.y * s.iz);
     }
-    atomicAdd(base, ax * ay * az * contrib);
-    atomicAdd(base + ox, s.fx * ay * az * contrib);
-    atomicAdd(base + oy, ax * s.fy * az * contrib);
-    atomicAdd(base + oy + ox, s.fx * s.fy * az * contrib);
-    atomicAdd(base + oz, ax * ay * s.fz * contrib);
-    atomicAdd(base + oz + ox, s.fx * ay * s.fz * contrib);
-    atomicAdd(base + oz + oy, ax * s.fy * s.fz * contrib);
-    atomicAdd(base + oz + oy + ox, s.fx * s.fy * s.fz * contrib);
+    // a zero weight leaves the cell unchanged, so its atomic is skipped: for integer sigma_s the fractions are multiples
+    // of 1/sigma_s and on average only 4.5 of the 8 corners carry weight at sigma_s = 2
+    const float w000 = ax * ay * az * contrib, w100 = s.fx * ay * az * contrib, w010 = ax * s.fy * az * contrib,
+                w110 = s.fx * s.fy * az * contrib, w001 = ax * ay * s.fz * contrib, w101 = s.fx * ay * s.fz * contrib,
+                w011 = ax * s.fy * s.fz * contrib, w111 = s.fx * s.fy * s.fz * contrib;
+    if (w000 != 0.0f) atomicAdd(base, w000);
+    if (w100 != 0.0f) atomicAdd(base + ox, w100);
+    if (w010 != 0.0f) atomicAdd(base + oy, w010);
+    if (w110 != 0.0f) atomicAdd(base + oy + ox, w110);
+    if (w001 != 0.0f) atomicAdd(base + oz, w001);
+    if (w101 != 0.0f) atomicAdd(base + oz + ox, w101);
+    if (w011 != 0.0f) atomicAdd(base + oz + oy, w011);
+    if (w111 != 0.0f) atomicAdd(base + oz + oy + ox, w111);
   }
   if (kPrivate) {
     __syncthreads();
@@ -110,45 +115,50 @@ __global__ void __launch_bounds__(kThreads) splat_kernel(const float *__restrict
   }
 }
 
-// fused x / y gaussian (1-4-6-4-1)/16 and z derivative (-2,-4,0,4,2)/16, zero beyond the grid (bilateral.cu:132-203)
-constexpr int BX = 32, BY = 8;
+// fused x / y gaussian (1-4-6-4-1)/16 and z derivative (-2,-4,0,4,2)/16, zero beyond the grid (bilateral.cu:132-203).
+// Thread (tx, ty) of a 32 x 8 CTA owns grid column (x, y): the x taps come straight from global memory (five coalesced,
+// L1-resident loads), the x-blurred rows of the 32 x 12 patch go through shared memory once, and the y blur feeds a
+// five-deep register window along z that produces the derivative: one barrier, no index arithmetic in the loops.
+constexpr int BX = 32, BY = 8, PYB = BY + 4;
 __global__ void __launch_bounds__(kThreads) blur_kernel(const float *__restrict__ in, float *__restrict__ out, GridDims g) {
-  extern __shared__ float sm[];
-  constexpr int PX = BX + 4, PY = BY + 4;
-  float *a = sm;                  // [z][PY][PX]  input patch
-  float *b = a + g.z * PY * PX;   // [z][PY][BX]  after x
-  const int cx0 = blockIdx.x * BX, cy0 = blockIdx.y * BY;
+  extern __shared__ float sm[];  // [z][PYB][BX] after the x pass
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = blockIdx.x * BX + tx, y0 = blockIdx.y * BY;
   const int64_t plane = (int64_t)g.x * g.y;
-  for (int i = threadIdx.x; i < g.z * PY * PX; i += kThreads) {
-    const int lx = i % PX, ly = (i / PX) % PY, z = i / (PX * PY);
-    const int x = cx0 - 2 + lx, y = cy0 - 2 + ly;
-    a[i] = (x >= 0 && y >= 0 && x < g.x && y < g.y) ? __ldg(in + x + (int64_t)g.x * y + plane * z) : 0.0f;
-  }
-  __syncthreads();
   const float w0 = 6.0f / 16.0f, w1 = 4.0f / 16.0f, w2 = 1.0f / 16.0f;
-  for (int i = threadIdx.x; i < g.z * PY * BX; i += kThreads) {
-    const int lx = i % BX, ly = (i / BX) % PY, z = i / (BX * PY);
-    const float *p = a + (z * PY + ly) * PX + lx + 2;
-    b[i] = p[0] * w0 + w1 * (p[1] + p[-1]) + w2 * (p[2] + p[-2]);
+  const bool xm2 = x - 2 >= 0 && x - 2 < g.x, xm1 = x - 1 >= 0 && x - 1 < g.x, xc = x < g.x, xp1 = x + 1 < g.x, xp2 = x + 2 < g.x;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int ly = ty + 8 * k;  // patch rows ty and ty + 8 (the latter only for ty < 4)
+    if (ly >= PYB) break;
+    const int y = y0 - 2 + ly;
+    const bool row = y >= 0 && y < g.y;
+    const float *p = in + (int64_t)y * g.x + x;
+    float *d = sm + ly * BX + tx;
+    for (int z = 0; z < g.z; z++, p += plane, d += PYB * BX) {
+      float v = 0.0f;
+      if (row) {
+        const float a = xm2 ? __ldg(p - 2) : 0.0f, b = xm1 ? __ldg(p - 1) : 0.0f, c = xc ? __ldg(p) : 0.0f;
+        const float e = xp1 ? __ldg(p + 1) : 0.0f, f = xp2 ? __ldg(p + 2) : 0.0f;
+        v = c * w0 + w1 * (e + b) + w2 * (f + a);
+      }
+      *d = v;
+    }
   }
   __syncthreads();
-  // y blur into a (reused as [z][BY][BX]); rows outside the grid must read as zero, which the x pass preserved
-  for (int i = threadIdx.x; i < g.z * BY * BX; i += kThreads) {
-    const int lx = i % BX, ly = (i / BX) % BY, z = i / (BX * BY);
-    const float *p = b + (z * PY + ly + 2) * BX + lx;
-    a[i] = p[0] * w0 + w1 * (p[BX] + p[-BX]) + w2 * (p[2 * BX] + p[-2 * BX]);
-  }
-  __syncthreads();
+  const int y = y0 + ty;
+  if (x >= g.x || y >= g.y) return;
   const float d1 = 4.0f / 16.0f, d2 = 2.0f / 16.0f;
-  for (int i = threadIdx.x; i < g.z * BY * BX; i += kThreads) {
-    const int lx = i % BX, ly = (i / BX) % BY, z = i / (BX * BY);
-    const int x = cx0 + lx, y = cy0 + ly;
-    if (x >= g.x || y >= g.y) continue;
-    const int zs = BY * BX;
-    const float *p = a + i;
-    const float p1 = z + 1 < g.z ? p[zs] : 0.0f, m1 = z >= 1 ? p[-zs] : 0.0f;
-    const float p2 = z + 2 < g.z ? p[2 * zs] : 0.0f, m2 = z >= 2 ? p[-2 * zs] : 0.0f;
-    out[x + (int64_t)g.x * y + plane * z] = d1 * (p1 - m1) + d2 * (p2 - m2);
+  const float *b = sm + (ty + 2) * BX + tx;
+  float *o = out + (int64_t)y * g.x + x;
+  // register window over z: m2, m1, c0, p1 hold the xy-blurred values at z-4 .. z-1 when plane z is read
+  float m2 = 0.0f, m1 = 0.0f, c0 = 0.0f, p1 = 0.0f;
+  for (int z = 0; z < g.z + 2; z++, b += PYB * BX) {
+    float p2 = 0.0f;
+    if (z < g.z) p2 = b[0] * w0 + w1 * (b[BX] + b[-BX]) + w2 * (b[2 * BX] + b[-2 * BX]);
+    // output plane z - 2: neighbours z-1 (p1), z-3 (m1), z (p2), z-4 (m2)
+    if (z >= 2) o[plane * (z - 2)] = d1 * (p1 - m1) + d2 * (p2 - m2);
+    m2 = m1, m1 = c0, c0 = p1, p1 = p2;
   }
 }
 
@@ -198,9 +208,9 @@ int run_bilateral(const float *in, float *out, void *scratch, int width, int hei
   if (int e = check_launch("bilateral_splat")) return e;
   {
     static bool attr = false;
-    const size_t bytes = (size_t)g.z * ((BX + 4) * (BY + 4) + (BY + 4) * BX) * sizeof(float);
+    const size_t bytes = (size_t)g.z * PYB * BX * sizeof(float);
     if (!attr) {
-      cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51 * ((BX + 4) * (BY + 4) + (BY + 4) * BX) * 4);
+      cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51 * PYB * BX * 4);
       attr = true;
     }
     dim3 bgrid(div_up(g.x, BX), div_up(g.y, BY));
