@@ -40,7 +40,7 @@ GRID_BPP = 4.0 * 1921 * 1081 * 6 / (WIDTH * HEIGHT)
 ALG_BYTES = {
   'rcd_demosaic': 13.5, 'color_smoothing': 24.0, 'green_eq_ratio': 0.0, 'green_equilibration': 24.0,
   'bounds_init': 0.0, 'compute_image_bounds': 12.0 / 64, 'lerp': 0.0, 'normalize': 24.0,
-  'wiener_log_luminance': 16.0, 'wiener_zero_accumulator': 4.0, 'wiener_tiles': 8.0, 'wiener_normalize': 28.0,
+  'wiener_log_luminance': 16.0, 'wiener_zero_accumulator': 4.0, 'wiener_tiles': 8.0, 'wiener_tiles_border': 0.0, 'rcd_demosaic_frame': 0.0, 'wiener_normalize': 28.0,
   'bilateral_zero_grid': GRID_BPP, 'bilateral_splat': 12.0 + GRID_BPP, 'bilateral_blur': 2 * GRID_BPP,
   'bilateral_slice': 24.0, 'metrics_init': 0.0, 'compute_image_metrics': 12.0 / 64, 'metrics_finalize': 0.0, 'tonemap': 15.0,
 }
