@@ -788,11 +788,7 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
   TileRects rects{};
   const int ntx = div_up(width, T), nty = div_up(height, T);
   if (aligned && bx_hi >= bx_lo && by_hi >= by_lo) {
-    dim3 grid2(bx_hi - bx_lo + 1, by_hi - by_lo + 1);
-    if (fc(0, 0, filters) == 1) v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
-    else v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
-    if (int e = check_launch("rcd_demosaic")) return e;
-    // the frame of 32 x 32 tiles around the v2 interior: top, bottom, left, right
+    // the frame of 32 x 32 tiles around the v2 interior: top, bottom, left, right -- on the side stream, next to the interior
     const int ix0 = bx_lo * v2::TW / T, ix1 = (bx_hi + 1) * v2::TW / T, iy0 = by_lo * v2::TH / T, iy1 = (by_hi + 1) * v2::TH / T;
     const int rx0[4] = {0, 0, 0, ix1}, ry0[4] = {0, iy1, iy0, iy0};
     const int rnx[4] = {ntx, ntx, ix0, ntx - ix1}, rny[4] = {iy0, nty - iy1, iy1 - iy0, iy1 - iy0};
@@ -805,11 +801,18 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     for (int k = n; k < 5; k++) rects.start[k] = total;
     for (int k = n; k < 4; k++) rects.ntx[k] = 1;
     rects.n = n;
+    cudaStream_t side = s;
     if (total > 0) {
-      rcd_kernel<<<total, kThreads, bytes, s>>>(src, rgb, width, height, filters, rects);
-      return check_launch("rcd_demosaic_frame");
+      side = fork_side(s);
+      rcd_kernel<<<total, kThreads, bytes, side>>>(src, rgb, width, height, filters, rects);
+      if (int e = check_launch("rcd_demosaic_frame")) return e;
     }
-    return TDB_OK;
+    dim3 grid2(bx_hi - bx_lo + 1, by_hi - by_lo + 1);
+    if (fc(0, 0, filters) == 1) v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
+    else v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
+    const int e = check_launch("rcd_demosaic");
+    join_side(s, side);
+    return e;
   }
   dim3 grid(ntx, nty);
   rcd_kernel<<<grid, kThreads, bytes, s>>>(src, rgb, width, height, filters, rects);

@@ -15,6 +15,9 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are siz
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
 void count_launches(int n);
+// a per-device side stream ordered after everything already queued on `main` (returns `main` itself when unavailable)
+cudaStream_t fork_side(cudaStream_t main);
+void join_side(cudaStream_t main, cudaStream_t side);
 
 #define TDB_REQUIRE(cond, ...)        \
   do {                                \

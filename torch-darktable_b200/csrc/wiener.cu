@@ -130,6 +130,7 @@ struct WienerArgs {
   int64_t njobs;       // grid_h * pairs_w * channels
   int px_lo, px_hi, gy_lo, gy_hi;  // K = 32: rectangle of tile pairs that lie fully inside the image (empty if px_hi < px_lo)
   int64_t njobs_interior;
+  unsigned int *counters;  // two job counters (interior, border) in the scratch buffer, zeroed with the accumulator
   float win[32];       // 1-D window (both the FFT and the interpolation window of the reference)
 };
 
@@ -266,11 +267,17 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
   // ncu showed 29 % of the stall samples waiting for instruction fetch); the border instantiation enumerates the rest.  All warps of a CTA run the same number of iterations and meet at a barrier per job, which
   // keeps the four warps of a scheduler in the same stretch of this long, loop-free instruction stream.
   const int64_t njobs = kBorder ? a.njobs - a.njobs_interior : a.njobs_interior;
-  const int64_t job0 = (int64_t)blockIdx.x * kWarps + warp, job_step = (int64_t)gridDim.x * kWarps;
-  const int64_t iters = (njobs + job_step - 1) / job_step;
-  for (int64_t it = 0; it < iters; it++) {
-    const int64_t job = job0 + it * job_step;
+  unsigned int *counter = a.counters + (kBorder ? 1 : 0);
+  __shared__ unsigned int s_base;
+  for (;;) {
+    // dynamic scheduling: a CTA claims kWarps consecutive jobs (neighbours in x: shared lines in L1) at a time, so CTAs that
+    // start late -- the border launch runs next to the interior one on the side stream -- simply claim fewer
     __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(counter, (unsigned int)kWarps);
+    __syncthreads();
+    const int64_t base = s_base;
+    if (base >= njobs) break;
+    const int64_t job = base + warp;
     if (job >= njobs) continue;  // whole warps: no divergence around the shuffles
     const int ch = (int)(job % cs);
     const int64_t t = job / cs;
@@ -475,7 +482,9 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   a.pairs_w = (a.grid_w + 1) / 2;
   a.njobs = (int64_t)a.grid_h * a.pairs_w * channels;
   make_window(tile, a.win);
-  cudaMemsetAsync(acc, 0, (size_t)width * height * channels * sizeof(float), s);
+  // scratch layout: [64 floats: job counters][accumulator][extra plane]; one memset clears counters and accumulator
+  a.counters = reinterpret_cast<unsigned int *>(acc) - 64;
+  cudaMemsetAsync(a.counters, 0, ((size_t)width * height * channels + 64) * sizeof(float), s);
   check_launch("wiener_zero_accumulator");
   const int sub = 32 / tile;
   const int64_t warps_needed = (a.njobs + sub - 1) / sub;
@@ -512,6 +521,17 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
       int64_t c = (jobs + kWarps - 1) / kWarps;  // persistent grid: two CTAs per SM
       return (int)(c > 2 * kNumSMs ? 2 * kNumSMs : (c < 1 ? 1 : c));
     };
+    cudaStream_t side = s;
+    if (a.njobs > a.njobs_interior) {  // border pairs on the side stream, next to the interior kernel
+      if (a.njobs_interior > 0) side = fork_side(s);
+      // a quarter of the CTA slots when it runs next to the interior kernel, the whole machine when it runs alone
+      const int g = side != s ? (grid_for(a.njobs - a.njobs_interior) < kNumSMs / 2 ? grid_for(a.njobs - a.njobs_interior) : kNumSMs / 2)
+                              : grid_for(a.njobs - a.njobs_interior);
+      if (st == 8) wiener32_kernel<8, true><<<g, kThreads, smem32, side>>>(a);
+      else if (st == 4) wiener32_kernel<4, true><<<g, kThreads, smem32, side>>>(a);
+      else wiener32_kernel<16, true><<<g, kThreads, smem32, side>>>(a);
+      if (int e = check_launch("wiener_tiles_border")) return e;
+    }
     if (a.njobs_interior > 0) {
       const int g = grid_for(a.njobs_interior);
       if (st == 8) wiener32_kernel<8, false><<<g, kThreads, smem32, s>>>(a);
@@ -519,12 +539,8 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
       else wiener32_kernel<16, false><<<g, kThreads, smem32, s>>>(a);
       if (int e = check_launch("wiener_tiles")) return e;
     }
-    if (a.njobs == a.njobs_interior) return TDB_OK;
-    const int g = grid_for(a.njobs - a.njobs_interior);
-    if (st == 8) wiener32_kernel<8, true><<<g, kThreads, smem32, s>>>(a);
-    else if (st == 4) wiener32_kernel<4, true><<<g, kThreads, smem32, s>>>(a);
-    else wiener32_kernel<16, true><<<g, kThreads, smem32, s>>>(a);
-    return check_launch("wiener_tiles_border");
+    join_side(s, side);
+    return TDB_OK;
   } else {
     wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
   }
@@ -550,7 +566,7 @@ size_t tdb_wiener_scratch_bytes(int width, int height, int channels, int tile) {
   (void)tile;
   if (width <= 0 || height <= 0) return 0;
   // accumulator (C planes interleaved) + one extra plane for the log-luminance composite
-  return ((size_t)width * height * (channels + 1)) * sizeof(float);
+  return ((size_t)width * height * (channels + 1)) * sizeof(float) + 256;  // + job counters of the K = 32 kernels
 }
 
 int tdb_wiener(const float *in, float *out, void *scratch, int width, int height, int channels, int tile, int overlap,
@@ -558,7 +574,7 @@ int tdb_wiener(const float *in, float *out, void *scratch, int width, int height
   TDB_REQUIRE(in && out && scratch && sigmas, "Wiener: null pointer");
   if (int e = check_args(width, height, channels, tile, overlap)) return e;
   cudaStream_t s = as_stream(stream);
-  float *acc = static_cast<float *>(scratch);
+  float *acc = static_cast<float *>(scratch) + 64;
   if (int e = run_tiles(in, acc, width, height, channels, tile, overlap, sigmas, 0.0f, s)) return e;
   NormArgs n{};
   n.acc = acc, n.rgb = nullptr, n.out = out, n.width = width, n.height = height, n.channels = channels, n.K = tile, n.stride = tile / overlap;
@@ -575,7 +591,7 @@ int tdb_wiener_log_luminance(const float *rgb, float *out, void *scratch, int wi
   TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
   if (int e = check_args(width, height, 1, tile, overlap)) return e;
   cudaStream_t s = as_stream(stream);
-  float *acc = static_cast<float *>(scratch);
+  float *acc = static_cast<float *>(scratch) + 64;
   float *lum = acc + (size_t)width * height;
   const int64_t px = (int64_t)width * height;
   const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
