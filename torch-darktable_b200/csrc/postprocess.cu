@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
   float *outt = (passes & 1) ? xpl : d0;    // the last pass reads D[(passes-1)&1]; the tile takes the other three planes
   float s1 = 0.0f, s2 = 0.0f;
   const int we = width & ~1, he = height & ~1;
+  // patch fully inside the image (and inside its even crop): no per-pixel tests in the passes
+  const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + SPW <= we && gy0 + PH <= he;
+  const int green_par = fc(0, 0, filters) == 1 ? 0 : 1;  // green sites: (x + y) & 1 == green_par
   for (int m = 1; m <= passes; m++) {
     const float *src = ((m - 1) & 1) ? d1 : d0;
     float *dst = (m & 1) ? d1 : d0;
@@ -118,25 +121,30 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
       Triple ra = sort3(pr[-1], pr[0], pr[1]), ba = sort3(pb[-1], pb[0], pb[1]);
       pr += SPW, pb += SPW;
       Triple rbt = sort3(pr[-1], pr[0], pr[1]), bbt = sort3(pb[-1], pb[0], pb[1]);
-      for (int r = rb; r < re; r++) {
+      float *pg = gpl + rb * SPW + col;
+      float *pd = dst + rb * SPW + col;
+      float *po = outt + 3 * ((rb - passes) * SW + (col - SHX));
+      const bool green_row0 = ((gx ^ gy0) & 1) == green_par;  // is (gx, patch row 0) a green site
+      for (int r = rb; r < re; r++, pg += SPW, pd += SPW, po += 3 * SW) {
         pr += SPW, pb += SPW;
         const Triple rc = sort3(pr[-1], pr[0], pr[1]), bc = sort3(pb[-1], pb[0], pb[1]);
+        const float mr = median_of_rows(ra, rbt, rc), mb = median_of_rows(ba, bbt, bc);
+        const float g = *pg;
+        float R = fmaxf(mr + g, 0.0f), B = fmaxf(mb + g, 0.0f), G = fmaxf(g, 0.0f);
         const int gy = gy0 + r;
-        float R = 0.0f, G = 0.0f, B = 0.0f;
-        if (col_in && gy >= 0 && gy < height) {  // outside stays zero for the next pass
-          const float mr = median_of_rows(ra, rbt, rc), mb = median_of_rows(ba, bbt, bc);
-          const float g = gpl[r * SPW + col];
-          R = fmaxf(mr + g, 0.0f), B = fmaxf(mb + g, 0.0f), G = fmaxf(g, 0.0f);
-        }
+        const bool pix_in = inside || (col_in && gy >= 0 && gy < height);
+        if (!pix_in) R = 0.0f, G = 0.0f, B = 0.0f;  // outside stays zero for the next pass
         if (!last) {
-          dst[r * SPW + col] = R - G, dst[plane + r * SPW + col] = B - G;
-          gpl[r * SPW + col] = G;
+          pd[0] = R - G, pd[plane] = B - G;
+          *pg = G;
         } else {
-          float *o = outt + 3 * ((r - passes) * SW + (col - SHX));
-          o[0] = R, o[1] = G, o[2] = B;
+          po[0] = R, po[1] = G, po[2] = B;
           // green sums over the even-cropped image (postprocess.cu:195-203)
-          if (want_sums && gx < we && gy < he && col_in && gy >= 0 && fc(gy & 1, gx & 1, filters) == 1) {
-            if (gy & 1) s2 += G; else s1 += G;
+          if (want_sums) {
+            const bool green = green_row0 != (bool)(r & 1);
+            const bool counted = green && (inside || (pix_in && gx < we && gy < he));
+            const float gs = counted ? G : 0.0f;
+            if (gy & 1) s2 += gs; else s1 += gs;
           }
         }
         ra = rbt, rbt = rc, ba = bbt, bbt = bc;

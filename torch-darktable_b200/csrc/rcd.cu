@@ -448,13 +448,13 @@ __device__ __forceinline__ void stage_group(const CfaSource &s, const uint8_t *r
 // kG0: the CFA site (even row, even column) is green, i.e. the R/B sites of even rows sit on odd columns
 template <bool kG0>
 __global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                            uint32_t filters, int bx_lo, int by_lo) {
+                                                            uint32_t filters, int x_origin, int by_lo) {
   extern __shared__ __align__(16) float sm[];
   float *cfa = sm + O_CFA, *vh = sm + O_VH, *lpf = sm + O_LPF, *crb = sm + O_CRB;
   float *vd = sm + O_VD, *hd = sm + O_HD, *pd = sm + O_PD, *qd = sm + O_QD, *pq = sm + O_PQ, *grb = sm + O_GRB;
   resolve_gains(src, filters);
   const int tid = threadIdx.x;
-  const int x0 = (blockIdx.x + bx_lo) * TW, y0 = (blockIdx.y + by_lo) * TH;
+  const int x0 = x_origin + blockIdx.x * TW, y0 = (blockIdx.y + by_lo) * TH;
   const int gx0 = x0 - HX, gy0 = y0 - HY;  // image coordinates of patch cell (0, 0): both even, gx0 a multiple of 4
 
   // ---- stage the CFA patch (clamped at zero like the reference's populate step)
@@ -779,17 +779,19 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     cudaFuncSetAttribute(v2::rcd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2);
     attr = true;
   }
-  // v2 tiles (64 x 32) whose 88 x 56 patch lies inside the image; needs 16-byte aligned rows on both sides
-  const int bx_lo = 1, bx_hi = (width - (v2::TW + v2::HX)) / v2::TW;     // 64 bx + 76 <= width
+  // v2 tiles (64 x 32) whose 88 x 56 patch lies inside the image; needs 16-byte aligned rows on both sides.  The tiling starts
+  // at x = 32 so that the frame left to the v1 kernel is a ring of single 32 x 32 tiles
+  const int x_origin = T;
+  const int nbx = (width - x_origin - (v2::TW + v2::HX)) / v2::TW + 1;   // x_origin + 64 bx + 76 <= width
   const int by_lo = 1, by_hi = (height - (v2::TH + v2::HY)) / v2::TH;    // 32 by + 44 <= height
   const bool aligned = (width % 4 == 0) && (reinterpret_cast<uintptr_t>(rgb) % 16 == 0) &&
                        (src.cfa ? reinterpret_cast<uintptr_t>(src.cfa) % 8 == 0
                                 : (reinterpret_cast<uintptr_t>(src.packed) % 4 == 0 && ((int64_t)width * height * 3 / 2) % 4 == 0));
   TileRects rects{};
   const int ntx = div_up(width, T), nty = div_up(height, T);
-  if (aligned && bx_hi >= bx_lo && by_hi >= by_lo) {
+  if (aligned && width >= x_origin + v2::TW + v2::HX && nbx >= 1 && by_hi >= by_lo) {
     // the frame of 32 x 32 tiles around the v2 interior: top, bottom, left, right -- on the side stream, next to the interior
-    const int ix0 = bx_lo * v2::TW / T, ix1 = (bx_hi + 1) * v2::TW / T, iy0 = by_lo * v2::TH / T, iy1 = (by_hi + 1) * v2::TH / T;
+    const int ix0 = x_origin / T, ix1 = (x_origin + nbx * v2::TW) / T, iy0 = by_lo * v2::TH / T, iy1 = (by_hi + 1) * v2::TH / T;
     const int rx0[4] = {0, 0, 0, ix1}, ry0[4] = {0, iy1, iy0, iy0};
     const int rnx[4] = {ntx, ntx, ix0, ntx - ix1}, rny[4] = {iy0, nty - iy1, iy1 - iy0, iy1 - iy0};
     int n = 0, total = 0;
@@ -807,9 +809,9 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
       rcd_kernel<<<total, kThreads, bytes, side>>>(src, rgb, width, height, filters, rects);
       if (int e = check_launch("rcd_demosaic_frame")) return e;
     }
-    dim3 grid2(bx_hi - bx_lo + 1, by_hi - by_lo + 1);
-    if (fc(0, 0, filters) == 1) v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
-    else v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, bx_lo, by_lo);
+    dim3 grid2(nbx, by_hi - by_lo + 1);
+    if (fc(0, 0, filters) == 1) v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo);
+    else v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo);
     const int e = check_launch("rcd_demosaic");
     join_side(s, side);
     return e;
