@@ -101,6 +101,12 @@ int tdb_demosaic_packed(const uint8_t *packed, float *rgb, int width, int height
 size_t tdb_postprocess_scratch_bytes(int width, int height);
 int tdb_postprocess(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
                     int green_eq_local, int green_eq_global, float green_eq_threshold, tdb_stream_t stream);
+/* The two halves of the global green equilibration (postprocess.cu:355-384) for a frame whose rows are split across GPUs
+ * (SURVEY.md 8e): sums[0..1] = green sums of the G1 / G2 sites of the given rows (the caller all-reduces them over the ranks
+ * and forms ratio = sums[1] / sums[0]), then the equilibration with that ratio (device float).  scratch as above.          */
+int tdb_green_sums(const float *rgb, int width, int height, uint32_t filters, void *scratch, float *sums, tdb_stream_t stream);
+int tdb_green_eq_apply(const float *in, float *out, int width, int height, uint32_t filters, int green_eq_local,
+                       float green_eq_threshold, const float *ratio, tdb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Colour ops (extension.cpp:127-156, csrc/color_conversions.cu, csrc/device_conversions.h).  npixels = H*W.  */

@@ -36,7 +36,7 @@ def test_binding_table_matches_header():
 def test_scratch_size_queries_need_no_gpu():
   from torch_darktable._lib import lib
   assert lib.tdb_postprocess_scratch_bytes(3840, 2160) >= 2 * 3840 * 2160 * 12
-  assert lib.tdb_wiener_scratch_bytes(3840, 2160, 1, 32) == 3840 * 2160 * 2 * 4
+  assert 0 <= lib.tdb_wiener_scratch_bytes(3840, 2160, 1, 32) - 3840 * 2160 * 2 * 4 <= 4096
   size = (ctypes.c_int * 3)()
   assert lib.tdb_bilateral_grid_size(4096, 3000, 2.0, 0.2, size) == 0
   assert tuple(size) == (2049, 1501, 6)

@@ -216,10 +216,10 @@ __global__ void __launch_bounds__(1024) ratio_kernel(const float *__restrict__ p
 // global ratio on G1 sites (+ clamp) and local equilibration of G2 sites (postprocess.cu:84-169, :234-255)
 __global__ void __launch_bounds__(kThreads) green_eq_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height,
                                                             uint32_t filters, int do_global, int do_local, float threshold,
-                                                            const Header *__restrict__ hdr) {
+                                                            const float *__restrict__ ratio_ptr) {
   constexpr int PW = T + 4;
   __shared__ float gsm[PW * PW];
-  const float ratio = do_global ? hdr->ratio : 1.0f;
+  const float ratio = do_global ? __ldg(ratio_ptr) : 1.0f;
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
   if (do_local) {
@@ -327,7 +327,7 @@ int tdb_postprocess(const float *in, float *out, void *scratch, int width, int h
   }
   if (eq) {
     green_eq_kernel<<<grid, kThreads, 0, s>>>(cur, out, width, height, filters, green_eq_global, green_eq_local,
-                                              (float)(green_eq_threshold / 100.), hdr);
+                                              (float)(green_eq_threshold / 100.), &hdr->ratio);
     return check_launch("green_equilibration");
   }
   if (passes == 0) {  // nothing to do: the reference still returns a copy
@@ -335,6 +335,33 @@ int tdb_postprocess(const float *in, float *out, void *scratch, int width, int h
     check_launch("postprocess_copy");
   }
   return TDB_OK;
+}
+
+// ---- pieces of the post-process for a frame that is split into row tiles across GPUs: the green sums of the rows a rank owns
+// (sums[0] = G1, sums[1] = G2; the caller all-reduces them and forms the ratio), and the green equilibration with a given ratio.
+int tdb_green_sums(const float *rgb, int width, int height, uint32_t filters, void *scratch, float *sums, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && scratch && sums && width > 0 && height > 0, "green_sums: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const size_t nblk = (size_t)div_up(width, T) * div_up(height, T);
+  char *base = static_cast<char *>(scratch);
+  Header *hdr = reinterpret_cast<Header *>(base);
+  float *partials = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256));
+  dim3 grid(div_up(width, T), div_up(height, T));
+  green_sums_kernel<<<grid, kThreads, 0, s>>>(rgb, width, height, filters, partials);
+  if (int e = check_launch("green_sums")) return e;
+  ratio_kernel<<<1, 1024, 0, s>>>(partials, (int)nblk, hdr);
+  if (int e = check_launch("green_eq_ratio")) return e;
+  cudaMemcpyAsync(sums, hdr, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  return check_launch("green_sums_copy");
+}
+
+int tdb_green_eq_apply(const float *in, float *out, int width, int height, uint32_t filters, int green_eq_local, float green_eq_threshold,
+                       const float *ratio, tdb_stream_t stream) {
+  TDB_REQUIRE(in && out && ratio && width > 0 && height > 0, "green_eq_apply: bad arguments");
+  dim3 grid(div_up(width, T), div_up(height, T));
+  green_eq_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(in, out, width, height, filters, 1, green_eq_local,
+                                                          (float)(green_eq_threshold / 100.), ratio);
+  return check_launch("green_equilibration");
 }
 
 }  // extern "C"

@@ -42,6 +42,8 @@ _SIGNATURES = {
   'tdb_demosaic_packed': (_I, [_P, _P, _I, _I, _I, _U32, _I, _F, _P, _F, _P]),
   'tdb_postprocess_scratch_bytes': (_SZ, [_I, _I]),
   'tdb_postprocess': (_I, [_P, _P, _P, _I, _I, _U32, _I, _I, _I, _F, _P]),
+  'tdb_green_sums': (_I, [_P, _I, _I, _U32, _P, _P, _P]),
+  'tdb_green_eq_apply': (_I, [_P, _P, _I, _I, _U32, _I, _F, _P, _P]),
   'tdb_color_convert': (_I, [_P, _P, _I64, _I, _F, _F, _F, _P]),
   'tdb_color_transform_3x3': (_I, [_P, _P, _I64, _P, _P]),
   'tdb_compute_luminance': (_I, [_P, _P, _I64, _P]),

@@ -505,6 +505,52 @@ def compute_image_metrics(images, stride: int = 8, min_gray: float = 1e-4, resca
   return metrics
 
 
+def image_metric_sums(images, stride: int = 8, min_gray: float = 1e-4) -> torch.Tensor:
+  """The six raw sums behind compute_image_metrics (log-gray, gray, r, g, b, count) -- what ranks all-reduce when one frame is
+  split across GPUs; `metrics_from_sums` finishes them."""
+  _require(len(images) > 0, 'images must be non-empty')
+  device = images[0].device
+  sums = torch.empty(6, dtype=torch.float32, device=device)
+  with torch.cuda.device(device):
+    s = _stream(device)
+    check(lib.tdb_metrics_init(_ptr(sums), s))
+    for img in images:
+      _check_image(img)
+      src = img.contiguous()
+      check(lib.tdb_metrics_accumulate(_ptr(src), src.size(1), src.size(0), int(stride), float(min_gray), None, _ptr(sums), s))
+  return sums
+
+
+def metrics_from_sums(sums: torch.Tensor) -> torch.Tensor:
+  metrics = torch.empty(5, dtype=torch.float32, device=sums.device)
+  with torch.cuda.device(sums.device):
+    check(lib.tdb_metrics_finalize(_ptr(sums.contiguous()), _ptr(metrics), _stream(sums.device)))
+  return metrics
+
+
+def green_sums(rgb: torch.Tensor, pattern) -> torch.Tensor:
+  """(G1 sum, G2 sum) of an (H, W, 3) image whose first row is an even row of the CFA (postprocess.cu:195-203)."""
+  _check_image(rgb)
+  src = rgb.contiguous()
+  h, w = src.size(0), src.size(1)
+  sums = torch.empty(2, dtype=torch.float32, device=src.device)
+  scratch = torch.empty(lib.tdb_postprocess_scratch_bytes(w, h), dtype=torch.uint8, device=src.device)
+  with torch.cuda.device(src.device):
+    check(lib.tdb_green_sums(_ptr(src), w, h, _filters(pattern), _ptr(scratch), _ptr(sums), _stream(src.device)))
+  return sums
+
+
+def green_eq_apply(rgb: torch.Tensor, ratio: torch.Tensor, pattern, green_eq_local: bool = False, green_eq_threshold: float = 0.04):
+  """Global green equilibration with a given G2/G1 ratio (one-element device tensor), optionally followed by the local one."""
+  _check_image(rgb)
+  src = rgb.contiguous()
+  out = torch.empty_like(src)
+  with torch.cuda.device(src.device):
+    check(lib.tdb_green_eq_apply(_ptr(src), _ptr(out), src.size(1), src.size(0), _filters(pattern), int(green_eq_local),
+                                 float(green_eq_threshold), _ptr(ratio.to(torch.float32).contiguous()), _stream(src.device)))
+  return out
+
+
 _TM = {'reinhard': 0, 'aces': 1, 'adaptive_aces': 2, 'linear': 3}
 _TF = {'none': 0, 'rotate_90': 1, 'rotate_180': 2, 'rotate_270': 3, 'transpose': 4, 'flip_horiz': 5, 'flip_vert': 6, 'transverse': 7}
 
@@ -677,6 +723,7 @@ extension = SimpleNamespace(
   bilinear5x5_demosaic=bilinear5x5_demosaic, apply_white_balance=apply_white_balance, estimate_white_balance=estimate_white_balance,
   # fused additions (not in the reference binding)
   unpack12_wb=unpack12_wb, demosaic_packed=demosaic_packed, normalize=normalize, lerp=lerp, tonemap=tonemap,
+  image_metric_sums=image_metric_sums, metrics_from_sums=metrics_from_sums, green_sums=green_sums, green_eq_apply=green_eq_apply,
   launch_count=launch_count,
 )
 

@@ -4,8 +4,9 @@ from .camera_settings import CameraSettings, load_camera_settings_from_dir, sett
 from .config import Debayer, ImageProcessingSettings, ToneMapper
 from .image_processor import ImageProcessor, ImageSizeMismatchError
 from .presets import get_preset, presets
+from .tiled import TiledFrameProcessor, halo_rows, partition_rows
 from .transform import ImageTransform, transform, transformed_size
 
 __all__ = ['CameraSettings', 'Debayer', 'ImageProcessingSettings', 'ImageProcessor', 'ImageSizeMismatchError', 'ImageTransform',
-           'ToneMapper', 'get_preset', 'load_camera_settings_from_dir', 'presets', 'settings_for_file', 'transform',
+           'TiledFrameProcessor', 'ToneMapper', 'get_preset', 'halo_rows', 'load_camera_settings_from_dir', 'partition_rows', 'presets', 'settings_for_file', 'transform',
            'transformed_size']
