@@ -43,6 +43,9 @@ ALG_BYTES = {
   'wiener_log_luminance': 16.0, 'wiener_zero_accumulator': 4.0, 'wiener_tiles': 8.0, 'wiener_tiles_border': 0.0, 'rcd_demosaic_frame': 0.0, 'wiener_normalize': 28.0,
   'bilateral_zero_grid': GRID_BPP, 'bilateral_splat': 12.0 + GRID_BPP, 'bilateral_blur': 2 * GRID_BPP,
   'bilateral_slice': 24.0, 'metrics_init': 0.0, 'compute_image_metrics': 12.0 / 64, 'metrics_finalize': 0.0, 'tonemap': 15.0,
+  # fused frame pipeline
+  'frame_prepare': 12.0 + 12.0 + 4.0 + 4.0, 'wiener_normalize_splat': 28.0 + GRID_BPP, 'metrics_sliced': 12.0 / 64,
+  'bilateral_slice_tonemap': 15.0,
 }
 
 

@@ -197,6 +197,51 @@ size_t tdb_laplacian_scratch_bytes(int width, int height);
 int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int height, float sigma, float shadows,
                   float highlights, float clarity, tdb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused frame pipeline: what ImageProcessor.process_image_set (pipeline/image_processor.py:284-300) runs when the
+ * post-process, the Wiener denoiser and the bilateral local contrast are enabled.  Same arithmetic per pixel as the stage
+ * calls above, rearranged so that every intermediate image crosses HBM once and no statistic needs a launch of its own:
+ *
+ *   A  tdb_postprocess_deferred     smoothing; leaves the green ratio of the frame and the bounds of the image set behind
+ *   B  tdb_frame_prepare            green equilibration + normalisation + log-luminance + accumulator clear, one pass
+ *   C  tdb_wiener_log_luminance_fused  Wiener tiles; the normalisation pass also splats the bilateral grid; grid blur
+ *   D  tdb_metrics_sliced           tone-mapping metrics of the bilateral output, evaluated at the sampled pixels only
+ *   E  tdb_bilateral_slice_tonemap  slice + modify_luminance + tone map + gamma + vibrance + uint8 + transform, one pass
+ *
+ * frame_state: tdb_frame_state_bytes() of device memory per ImageProcessor, zero-filled ONCE by the caller (the last CTA
+ * of the kernels that gather statistics reduces their per-CTA partials and resets its own ticket).  An image set is a run of
+ * frames bracketed by first_in_set / last_in_set; bounds_out / metrics_out are written on the last frame as
+ * prev + (value - prev) * moving_average (prev == NULL: the value itself), i.e. pipeline/util.py:4 lerp.                 */
+size_t tdb_frame_state_bytes(void);
+/* scratch: tdb_postprocess_scratch_bytes().  out: smoothed image, green equilibration NOT applied.  ratio_out: device
+ * float[1], sum(G2)/sum(G1) of this frame (postprocess.cu:355-366).  bounds: over every bounds_stride-th pixel of the
+ * EQUILIBRATED image (compute_image_bounds semantics; x -> max(0, x * ratio) is monotone, so extrema commute with it).  */
+int tdb_postprocess_deferred(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
+                             int bounds_stride, void *frame_state, int first_in_set, int last_in_set, const float *prev_bounds,
+                             float moving_average, float *bounds_out, float *ratio_out, tdb_stream_t stream);
+/* out = normalize(green_eq_global(rgb, ratio), bounds); ratio == NULL skips the equilibration.  wiener_scratch != NULL:
+ * also writes log(max(eps, L(out))) into the scratch's luminance plane and clears its accumulator and job counters.      */
+int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch, int width, int height, uint32_t filters,
+                      const float *ratio, const float *bounds, float eps, tdb_stream_t stream);
+/* tdb_wiener_log_luminance with two options: prepared != 0 = the scratch was filled by tdb_frame_prepare;
+ * bilateral_scratch != NULL = also build the blurred bilateral grid of the OUTPUT image there (zero + splat + blur).     */
+int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap,
+                                   float noise, float eps, int prepared, void *bilateral_scratch, float sigma_s, float sigma_r,
+                                   tdb_stream_t stream);
+/* compute_image_metrics(stride, min_gray) of Bilateral.process_rgb(rgb, detail) given the blurred grid in
+ * bilateral_scratch (NULL: of rgb itself), accumulated over the image set.  metrics_out: device float[5].                */
+int tdb_metrics_sliced(const float *rgb, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r,
+                       float detail, int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set,
+                       const float *prev_metrics, float moving_average, float *metrics_out, tdb_stream_t stream);
+/* tdb_tonemap of Bilateral.process_rgb(rgb, detail) given the blurred grid in bilateral_scratch.                         */
+int tdb_bilateral_slice_tonemap(const float *rgb, const void *bilateral_scratch, uint8_t *out, int width, int height,
+                                float sigma_s, float sigma_r, float detail, int op, const float *metrics, float gamma,
+                                float intensity, float light_adapt, float vibrance, const float *matrix, int transform,
+                                tdb_stream_t stream);
+/* the first half of tdb_bilateral_rgb: zero + splat + blur, leaving the blurred grid in scratch                          */
+int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int height, float sigma_s, float sigma_r,
+                           tdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

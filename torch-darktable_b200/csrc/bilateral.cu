@@ -10,48 +10,15 @@
 //           instead of 24 B/cell), thread-x along the contiguous x axis;
 //   slice : trilinear gather; the RGB variant recomputes L and applies modify_luminance in the same pass.
 // Algorithmic traffic: lum->lum 12 B/px, rgb->rgb 36 B/px, plus 2 x grid.
-#include "color_math.cuh"
+#include "bilateral.cuh"
 
 namespace tdb {
 namespace {
 
+using namespace bil;
+
 constexpr int kThreads = 256;
 constexpr int TP = 64;  // splat pixel tile edge
-constexpr int kMaxSplatCells = 24000;
-
-struct GridDims {
-  int x, y, z;
-};
-
-static inline float clampf_host(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// reference bilateral.cu:273-299
-static GridDims grid_dims(int width, int height, float sigma_s, float sigma_r) {
-  float ss = sigma_s;
-  if (ss < 0.5f) ss = 0.5f;
-  const float gx = clampf_host(roundf(width / ss), 4.0f, 3000.0f);
-  const float gy = clampf_host(roundf(height / ss), 4.0f, 3000.0f);
-  const float gz = clampf_host(roundf(1.0f / sigma_r), 4.0f, 50.0f);
-  const float eff_s = fmaxf(height / gy, width / gx), eff_r = 1.0f / gz;
-  return GridDims{(int)ceilf(width / eff_s) + 1, (int)ceilf(height / eff_s) + 1, (int)ceilf(1.0f / eff_r) + 1};
-}
-
-struct Sample {
-  int ix, iy, iz;
-  float fx, fy, fz;
-};
-
-// reference bilateral.cu:71-86: coordinates use the RAW sigmas and saturate at the last cell
-__device__ __forceinline__ Sample make_sample(int x, int y, float L, GridDims g, float sigma_s, float sigma_r) {
-  const float gx = fminf(fmaxf(x / sigma_s, 0.0f), (float)(g.x - 1));
-  const float gy = fminf(fmaxf(y / sigma_s, 0.0f), (float)(g.y - 1));
-  const float gz = fminf(fmaxf(L / sigma_r, 0.0f), (float)(g.z - 1));
-  Sample s;
-  s.ix = min((int)gx, g.x - 2), s.iy = min((int)gy, g.y - 2), s.iz = min((int)gz, g.z - 2);
-  s.fx = gx - (float)s.ix, s.fy = gy - (float)s.iy, s.fz = gz - (float)s.iz;
-  return s;
-}
-__device__ __forceinline__ int cell_of(int p, float sigma_s, int n) { return min((int)fminf(fmaxf(p / sigma_s, 0.0f), (float)(n - 1)), n - 2); }
 
 template <bool kRgb>
 __device__ __forceinline__ float load_lum(const float *__restrict__ in, int64_t idx) {
@@ -59,59 +26,18 @@ __device__ __forceinline__ float load_lum(const float *__restrict__ in, int64_t 
   return __ldg(in + idx);
 }
 
-template <bool kRgb, bool kPrivate>
+template <bool kRgb>
 __global__ void __launch_bounds__(kThreads) splat_kernel(const float *__restrict__ in, float *__restrict__ grid, int width, int height,
                                                          GridDims g, float sigma_s, float sigma_r) {
-  extern __shared__ float cells[];
+  // (a CTA-private copy of the cells in shared memory was tried: shared-memory float atomicAdd compiles to a CAS spin loop on
+  // sm_100a, ATOMS.CAST.SPIN, and loses to native red.global.add.f32 on an L2-resident grid)
   const int x0 = blockIdx.x * TP, y0 = blockIdx.y * TP;
   const int x1 = min(x0 + TP, width), y1 = min(y0 + TP, height);
-  const float contrib = 1.0f / (sigma_s * sigma_s);
-  int cx0 = 0, cy0 = 0, ncx = 0, ncy = 0;
-  if (kPrivate) {
-    cx0 = cell_of(x0, sigma_s, g.x), cy0 = cell_of(y0, sigma_s, g.y);
-    ncx = cell_of(x1 - 1, sigma_s, g.x) + 2 - cx0, ncy = cell_of(y1 - 1, sigma_s, g.y) + 2 - cy0;
-    for (int i = threadIdx.x; i < ncx * ncy * g.z; i += kThreads) cells[i] = 0.0f;
-    __syncthreads();
-  }
   const int tw = x1 - x0, th = y1 - y0;
   for (int i = threadIdx.x; i < tw * th; i += kThreads) {
     const int ly = i / tw, lx = i - ly * tw;
     const int x = x0 + lx, y = y0 + ly;
-    const float L = load_lum<kRgb>(in, (int64_t)y * width + x);
-    const Sample s = make_sample(x, y, L, g, sigma_s, sigma_r);
-    const float ax = 1.0f - s.fx, ay = 1.0f - s.fy, az = 1.0f - s.fz;
-    float *base;
-    int ox, oy, oz;
-    if (kPrivate) {
-      ox = 1, oy = ncx, oz = ncx * ncy;
-      base = cells + (s.ix - cx0) + ncx * ((s.iy - cy0) + ncy * s.iz);
-    } else {
-      ox = 1, oy = g.x, oz = g.x * g.y;
-      base = grid + s.ix + (int64_t)g.x * (s.iy + (int64_t)g.y * s.iz);
-    }
-    // a zero weight leaves the cell unchanged, so its atomic is skipped: for integer sigma_s the fractions are multiples
-    // of 1/sigma_s and on average only 4.5 of the 8 corners carry weight at sigma_s = 2
-    const float w000 = ax * ay * az * contrib, w100 = s.fx * ay * az * contrib, w010 = ax * s.fy * az * contrib,
-                w110 = s.fx * s.fy * az * contrib, w001 = ax * ay * s.fz * contrib, w101 = s.fx * ay * s.fz * contrib,
-                w011 = ax * s.fy * s.fz * contrib, w111 = s.fx * s.fy * s.fz * contrib;
-    if (w000 != 0.0f) atomicAdd(base, w000);
-    if (w100 != 0.0f) atomicAdd(base + ox, w100);
-    if (w010 != 0.0f) atomicAdd(base + oy, w010);
-    if (w110 != 0.0f) atomicAdd(base + oy + ox, w110);
-    if (w001 != 0.0f) atomicAdd(base + oz, w001);
-    if (w101 != 0.0f) atomicAdd(base + oz + ox, w101);
-    if (w011 != 0.0f) atomicAdd(base + oz + oy, w011);
-    if (w111 != 0.0f) atomicAdd(base + oz + oy + ox, w111);
-  }
-  if (kPrivate) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < ncx * ncy * g.z; i += kThreads) {
-      const float v = cells[i];
-      if (v != 0.0f) {
-        const int lx = i % ncx, ly = (i / ncx) % ncy, lz = i / (ncx * ncy);
-        atomicAdd(grid + (cx0 + lx) + (int64_t)g.x * ((cy0 + ly) + (int64_t)g.y * lz), v);
-      }
-    }
+    splat_pixel(grid, x, y, load_lum<kRgb>(in, (int64_t)y * width + x), g, sigma_s, sigma_r);
   }
 }
 
@@ -168,28 +94,11 @@ __global__ void __launch_bounds__(kThreads) slice_kernel(const float *__restrict
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= width || y >= height) return;
   const int64_t idx = (int64_t)y * width + x;
-  rgb_t c{0, 0, 0};
-  float L;
   if (kRgb) {
-    c = rgb_t{__ldg(in + 3 * idx), __ldg(in + 3 * idx + 1), __ldg(in + 3 * idx + 2)};
-    L = pub::luminance(c);
-  } else {
-    L = __ldg(in + idx);
-  }
-  const Sample s = make_sample(x, y, L, g, sigma_s, sigma_r);
-  const float ax = 1.0f - s.fx, ay = 1.0f - s.fy, az = 1.0f - s.fz;
-  const int64_t oy = g.x, oz = (int64_t)g.x * g.y;
-  const float *p = grid + s.ix + oy * s.iy + oz * s.iz;
-  const float d = __ldg(p) * ax * ay * az + __ldg(p + 1) * s.fx * ay * az + __ldg(p + oy) * ax * s.fy * az +
-                  __ldg(p + oy + 1) * s.fx * s.fy * az + __ldg(p + oz) * ax * ay * s.fz + __ldg(p + oz + 1) * s.fx * ay * s.fz +
-                  __ldg(p + oz + oy) * ax * s.fy * s.fz + __ldg(p + oz + oy + 1) * s.fx * s.fy * s.fz;
-  const float norm = -detail * sigma_r * 4.0f;
-  const float Lout = fmaxf(0.0f, L + norm * d);
-  if (kRgb) {
-    const rgb_t r = pub::with_luminance(c, Lout);
+    const rgb_t r = slice_rgb(grid, x, y, rgb_t{__ldg(in + 3 * idx), __ldg(in + 3 * idx + 1), __ldg(in + 3 * idx + 2)}, g, sigma_s, sigma_r, detail);
     out[3 * idx] = r.x, out[3 * idx + 1] = r.y, out[3 * idx + 2] = r.z;
   } else {
-    out[idx] = Lout;
+    out[idx] = slice_luminance(grid, x, y, __ldg(in + idx), g, sigma_s, sigma_r, detail);
   }
 }
 
@@ -199,30 +108,37 @@ int run_bilateral(const float *in, float *out, void *scratch, int width, int hei
   const GridDims g = grid_dims(width, height, sigma_s, sigma_r);
   const size_t cells = (size_t)g.x * g.y * g.z;
   float *grid = static_cast<float *>(scratch), *blurred = grid + cells;
-  cudaMemsetAsync(grid, 0, cells * sizeof(float), s);
-  check_launch("bilateral_zero_grid");
-  // Shared-memory float atomicAdd compiles to a CAS spin loop on sm_100a (ATOMS.CAST.SPIN), so the privatised splat
-  // variant is not used; red.global.add.f32 is native and the grid is L2-resident for the common sigma_s.
+  if (int e = bilateral_zero_grid(scratch, g, s)) return e;
   dim3 sgrid(div_up(width, TP), div_up(height, TP));
-  splat_kernel<kRgb, false><<<sgrid, kThreads, 0, s>>>(in, grid, width, height, g, sigma_s, sigma_r);
+  splat_kernel<kRgb><<<sgrid, kThreads, 0, s>>>(in, grid, width, height, g, sigma_s, sigma_r);
   if (int e = check_launch("bilateral_splat")) return e;
-  {
-    static bool attr = false;
-    const size_t bytes = (size_t)g.z * PYB * BX * sizeof(float);
-    if (!attr) {
-      cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51 * PYB * BX * 4);
-      attr = true;
-    }
-    dim3 bgrid(div_up(g.x, BX), div_up(g.y, BY));
-    blur_kernel<<<bgrid, kThreads, bytes, s>>>(grid, blurred, g);
-    if (int e = check_launch("bilateral_blur")) return e;
-  }
+  if (int e = bilateral_blur(scratch, g, s)) return e;
   dim3 pgrid(div_up(width, 32), div_up(height, 8));
   slice_kernel<kRgb><<<pgrid, kThreads, 0, s>>>(in, blurred, out, width, height, g, sigma_s, sigma_r, detail);
   return check_launch("bilateral_slice");
 }
 
 }  // namespace
+
+int bilateral_zero_grid(void *scratch, bil::GridDims g, cudaStream_t s) {
+  cudaMemsetAsync(scratch, 0, (size_t)g.x * g.y * g.z * sizeof(float), s);
+  return check_launch("bilateral_zero_grid");
+}
+
+int bilateral_blur(void *scratch, bil::GridDims g, cudaStream_t s) {
+  static bool attr = false;
+  const size_t cells = (size_t)g.x * g.y * g.z;
+  float *grid = static_cast<float *>(scratch), *blurred = grid + cells;
+  const size_t bytes = (size_t)g.z * PYB * BX * sizeof(float);
+  if (!attr) {
+    cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51 * PYB * BX * 4);
+    attr = true;
+  }
+  dim3 bgrid(div_up(g.x, BX), div_up(g.y, BY));
+  blur_kernel<<<bgrid, kThreads, bytes, s>>>(grid, blurred, g);
+  return check_launch("bilateral_blur");
+}
+
 }  // namespace tdb
 
 using namespace tdb;
@@ -254,6 +170,18 @@ int tdb_bilateral_rgb(const float *rgb, float *out, void *scratch, int width, in
   TDB_REQUIRE(rgb && out && scratch, "Bilateral: null pointer");
   TDB_REQUIRE(width > 0 && height > 0 && sigma_r > 0.0f && sigma_s > 0.0f, "Bilateral: invalid dimensions or sigmas");
   return run_bilateral<true>(rgb, out, scratch, width, height, sigma_s, sigma_r, detail, as_stream(stream));
+}
+
+int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int height, float sigma_s, float sigma_r, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && scratch, "Bilateral: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0 && sigma_r > 0.0f && sigma_s > 0.0f, "Bilateral: invalid dimensions or sigmas");
+  cudaStream_t s = as_stream(stream);
+  const bil::GridDims g = bil::grid_dims(width, height, sigma_s, sigma_r);
+  if (int e = bilateral_zero_grid(scratch, g, s)) return e;
+  dim3 sgrid(div_up(width, TP), div_up(height, TP));
+  splat_kernel<true><<<sgrid, kThreads, 0, s>>>(rgb, static_cast<float *>(scratch), width, height, g, sigma_s, sigma_r);
+  if (int e = check_launch("bilateral_splat")) return e;
+  return bilateral_blur(scratch, g, s);
 }
 
 }  // extern "C"

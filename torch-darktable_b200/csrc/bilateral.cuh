@@ -1,0 +1,106 @@
+// Bilateral-grid geometry and the trilinear slice, shared by bilateral.cu and the fused slice + tone-map kernel (tonemap.cu).
+#pragma once
+
+#include <cmath>
+
+#include "color_math.cuh"
+
+namespace tdb {
+namespace bil {
+
+struct GridDims {
+  int x, y, z;
+};
+
+inline float clampf_host(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// reference bilateral.cu:273-299
+inline GridDims grid_dims(int width, int height, float sigma_s, float sigma_r) {
+  float ss = sigma_s;
+  if (ss < 0.5f) ss = 0.5f;
+  const float gx = clampf_host(roundf(width / ss), 4.0f, 3000.0f);
+  const float gy = clampf_host(roundf(height / ss), 4.0f, 3000.0f);
+  const float gz = clampf_host(roundf(1.0f / sigma_r), 4.0f, 50.0f);
+  const float eff_s = fmaxf(height / gy, width / gx), eff_r = 1.0f / gz;
+  return GridDims{(int)ceilf(width / eff_s) + 1, (int)ceilf(height / eff_s) + 1, (int)ceilf(1.0f / eff_r) + 1};
+}
+
+struct Sample {
+  int ix, iy, iz;
+  float fx, fy, fz;
+};
+
+// reference bilateral.cu:71-86: coordinates use the RAW sigmas and saturate at the last cell
+__device__ __forceinline__ Sample make_sample(int x, int y, float L, GridDims g, float sigma_s, float sigma_r) {
+  const float gx = fminf(fmaxf(x / sigma_s, 0.0f), (float)(g.x - 1));
+  const float gy = fminf(fmaxf(y / sigma_s, 0.0f), (float)(g.y - 1));
+  const float gz = fminf(fmaxf(L / sigma_r, 0.0f), (float)(g.z - 1));
+  Sample s;
+  s.ix = min((int)gx, g.x - 2), s.iy = min((int)gy, g.y - 2), s.iz = min((int)gz, g.z - 2);
+  s.fx = gx - (float)s.ix, s.fy = gy - (float)s.iy, s.fz = gz - (float)s.iz;
+  return s;
+}
+__device__ __forceinline__ int cell_of(int p, float sigma_s, int n) { return min((int)fminf(fmaxf(p / sigma_s, 0.0f), (float)(n - 1)), n - 2); }
+
+
+// trilinear gather of the blurred grid at (x, y, L) and the contrast step (reference bilateral.cu:206-249):
+// L' = max(0, L - detail * sigma_r * 4 * d)
+__device__ __forceinline__ float slice_luminance(const float *__restrict__ grid, int x, int y, float L, GridDims g, float sigma_s,
+                                                 float sigma_r, float detail) {
+  const Sample s = make_sample(x, y, L, g, sigma_s, sigma_r);
+  const float ax = 1.0f - s.fx, ay = 1.0f - s.fy, az = 1.0f - s.fz;
+  const int64_t oy = g.x, oz = (int64_t)g.x * g.y;
+  const float *p = grid + s.ix + oy * s.iy + oz * s.iz;
+  const float d = __ldg(p) * ax * ay * az + __ldg(p + 1) * s.fx * ay * az + __ldg(p + oy) * ax * s.fy * az +
+                  __ldg(p + oy + 1) * s.fx * s.fy * az + __ldg(p + oz) * ax * ay * s.fz + __ldg(p + oz + 1) * s.fx * ay * s.fz +
+                  __ldg(p + oz + oy) * ax * s.fy * s.fz + __ldg(p + oz + oy + 1) * s.fx * s.fy * s.fz;
+  const float norm = -detail * sigma_r * 4.0f;
+  return fmaxf(0.0f, L + norm * d);
+}
+
+// Bilateral.process_rgb for one pixel: Lab L of the colour -> slice -> modify_luminance (local_contrast.py:110-114).
+// compute_luminance clips the colour first; for a colour inside [0,1]^3 (always, after the Wiener write-back) the clip is the
+// identity and its L is the L of the rgb_to_lab that modify_luminance needs anyway, so the linearisation and lab_f(Y) -- four of the
+// thirteen pow() of this step -- are evaluated once.  Colours outside the cube take the literal path.
+__device__ __forceinline__ rgb_t slice_rgb(const float *__restrict__ grid, int x, int y, rgb_t c, GridDims g, float sigma_s, float sigma_r,
+                                           float detail) {
+  const bool inside = c.x >= 0.0f && c.x <= 1.0f && c.y >= 0.0f && c.y <= 1.0f && c.z >= 0.0f && c.z <= 1.0f;
+  const rgb_t v = pub::rgb_to_xyz(c);
+  const float fx = pub::lab_f(v.x / 0.95047f), fy = pub::lab_f(v.y / 1.0f), fz = pub::lab_f(v.z / 1.08883f);
+  float L = fmaxf(0.0f, (116.0f / 100.0f) * fy - (16.0f / 100.0f));
+  if (!inside) L = pub::luminance(c);
+  const float Lout = slice_luminance(grid, x, y, L, g, sigma_s, sigma_r, detail);
+  const rgb_t lab{fmaxf(0.0f, fminf(1.0f, Lout)), (500.0f / 128.0f) * (fx - fy), (200.0f / 128.0f) * (fy - fz)};
+  return clip01(pub::lab_to_rgb(lab));
+}
+
+// splat of one pixel into the grid with native red.global.add.f32 (reference bilateral.cu:89-129).  A zero weight leaves the cell
+// unchanged, so its atomic is skipped: for integer sigma_s the fractions are multiples of 1/sigma_s and on average only 4.5 of the 8
+// corners carry weight at sigma_s = 2
+__device__ __forceinline__ void splat_pixel(float *__restrict__ grid, int x, int y, float L, GridDims g, float sigma_s, float sigma_r) {
+  const float contrib = 1.0f / (sigma_s * sigma_s);
+  const Sample s = make_sample(x, y, L, g, sigma_s, sigma_r);
+  const float ax = 1.0f - s.fx, ay = 1.0f - s.fy, az = 1.0f - s.fz;
+  const int ox = 1, oy = g.x;
+  const int64_t oz = (int64_t)g.x * g.y;
+  float *base = grid + s.ix + (int64_t)g.x * (s.iy + (int64_t)g.y * s.iz);
+  const float w000 = ax * ay * az * contrib, w100 = s.fx * ay * az * contrib, w010 = ax * s.fy * az * contrib,
+              w110 = s.fx * s.fy * az * contrib, w001 = ax * ay * s.fz * contrib, w101 = s.fx * ay * s.fz * contrib,
+              w011 = ax * s.fy * s.fz * contrib, w111 = s.fx * s.fy * s.fz * contrib;
+  if (w000 != 0.0f) atomicAdd(base, w000);
+  if (w100 != 0.0f) atomicAdd(base + ox, w100);
+  if (w010 != 0.0f) atomicAdd(base + oy, w010);
+  if (w110 != 0.0f) atomicAdd(base + oy + ox, w110);
+  if (w001 != 0.0f) atomicAdd(base + oz, w001);
+  if (w101 != 0.0f) atomicAdd(base + oz + ox, w101);
+  if (w011 != 0.0f) atomicAdd(base + oz + oy, w011);
+  if (w111 != 0.0f) atomicAdd(base + oz + oy + ox, w111);
+}
+
+}  // namespace bil
+
+// host-side pieces of bilateral.cu used by the fused frame pipeline (scratch = [splat grid][blurred grid])
+int bilateral_zero_grid(void *scratch, bil::GridDims g, cudaStream_t s);
+int bilateral_blur(void *scratch, bil::GridDims g, cudaStream_t s);
+
+}  // namespace tdb

@@ -1,0 +1,210 @@
+// Pointwise glue of the fused frame pipeline (include/tdb200.h, "Fused frame pipeline").
+//
+//   frame_prepare  : global green equilibration (the ratio comes from the smoothing kernel's statistics) + normalisation with the
+//                    image-set bounds + log-luminance for the Wiener tiles + clearing of the Wiener accumulator, in one pass:
+//                    12 B read, 12 + 4 + 4 B written per pixel.  Replaces green_eq_kernel -> normalize_kernel -> loglum_kernel
+//                    -> memset (24 + 24 + 16 + 4 B/px, four launches); the arithmetic per pixel is the same, term by term.
+//   metrics_sliced : compute_image_metrics (color_adaption.cu:121-166) of the image the bilateral slice WOULD produce, evaluated
+//                    only at the sampled pixels (every stride-th), so that the slice itself can be fused into the tone-map kernel
+//                    and the locally contrasted image never exists in HBM.  The last CTA merges the sums into the image set and
+//                    applies the moving average (image_processor.py:292-294).
+#include "bilateral.cuh"
+#include "frame_state.cuh"
+#include "wiener_layout.cuh"
+
+namespace tdb {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int flat_grid(int64_t items) {
+  const int64_t want = (items + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+struct PrepareArgs {
+  const float *in;
+  float *out;
+  float *loglum;        // or null
+  float *zero;          // plane to clear (the Wiener accumulator), or null
+  unsigned int *counters;  // two job counters of the Wiener tile kernels to clear, or null
+  const float *ratio;   // device float[1], or null = no equilibration
+  const float *bounds;  // device float[2]
+  int width, height;
+  uint32_t filters;
+  float eps;
+};
+
+__device__ __forceinline__ rgb_t prepare_pixel(rgb_t c, bool g1, bool eq, float ratio, float b0, float range) {
+  if (eq) {  // green_eq_kernel (global part): G1 sites take the ratio, everything is clamped at zero
+    c.y *= g1 ? ratio : 1.0f;
+    c.x = fmaxf(c.x, 0.0f), c.y = fmaxf(c.y, 0.0f), c.z = fmaxf(c.z, 0.0f);
+  }
+  return rgb_t{(c.x - b0) / range, (c.y - b0) / range, (c.z - b0) / range};  // normalize_kernel
+}
+__device__ __forceinline__ float log_luminance(rgb_t c, float eps) { return logf(fmaxf(eps, pub::luminance(c))); }
+
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) {
+  const bool eq = a.ratio != nullptr;
+  const float ratio = eq ? __ldg(a.ratio) : 1.0f;
+  const float b0 = __ldg(a.bounds), range = __ldg(a.bounds + 1) - b0;
+  const int64_t n = (int64_t)a.width * a.height;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t t0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  // G1 sites: green sites of even rows.  (row 0, col 0) green -> even columns, else odd columns
+  const int g1_col = fc(0, 0, a.filters) == 1 ? 0 : 1;
+  if (t0 < 2 && a.counters) a.counters[t0] = 0u;
+  if (kVec) {  // width % 4 == 0: a 4-pixel group stays inside one row and starts on an even column
+    const int wq = a.width >> 2;
+    for (int64_t g = t0; g < n / 4; g += stride) {
+      const int y = (int)(g / wq);
+      const bool even_row = !(y & 1);
+      const float4 *src = reinterpret_cast<const float4 *>(a.in) + 3 * g;
+      rgb_t p[4];
+      unpack4(ld_stream(src), ld_stream(src + 1), ld_stream(src + 2), p);
+#pragma unroll
+      for (int k = 0; k < 4; k++) p[k] = prepare_pixel(p[k], even_row && ((k & 1) == g1_col), eq, ratio, b0, range);
+      float4 o0, o1, o2;
+      pack4(p, o0, o1, o2);
+      float4 *dst = reinterpret_cast<float4 *>(a.out) + 3 * g;
+      dst[0] = o0, dst[1] = o1, dst[2] = o2;
+      if (a.loglum)
+        reinterpret_cast<float4 *>(a.loglum)[g] =
+            make_float4(log_luminance(p[0], a.eps), log_luminance(p[1], a.eps), log_luminance(p[2], a.eps), log_luminance(p[3], a.eps));
+      if (a.zero) reinterpret_cast<float4 *>(a.zero)[g] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  } else {
+    for (int64_t i = t0; i < n; i += stride) {
+      const int y = (int)(i / a.width), x = (int)(i - (int64_t)y * a.width);
+      const rgb_t p = prepare_pixel(rgb_t{a.in[3 * i], a.in[3 * i + 1], a.in[3 * i + 2]}, !(y & 1) && ((x & 1) == g1_col), eq, ratio, b0, range);
+      a.out[3 * i] = p.x, a.out[3 * i + 1] = p.y, a.out[3 * i + 2] = p.z;
+      if (a.loglum) a.loglum[i] = log_luminance(p, a.eps);
+      if (a.zero) a.zero[i] = 0.0f;
+    }
+  }
+}
+
+struct MetricsArgs {
+  const float *rgb;
+  const float *grid;  // blurred bilateral grid, or null = measure rgb as it is
+  bil::GridDims g;
+  float sigma_s, sigma_r, detail;
+  int width, height, stride, sw;
+  int64_t nsamples;
+  float min_gray;
+  FrameState *state;
+  int first_in_set, last_in_set;
+  const float *prev_metrics;  // EMA state (device float[5]) or null
+  float moving_average;
+  float *metrics_out;         // device float[5], written on the last frame of a set
+};
+
+__global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsArgs a) {
+  // same arithmetic as metrics_kernel (pointwise.cu) with bounds = (0, 1)
+  const float b0 = 0.0f, range = 1.0f - b0 + 1e-6f;
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  const int64_t step = (int64_t)gridDim.x * kThreads;
+  for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < a.nsamples; s += step) {
+    const int sy = (int)(s / a.sw), sx = (int)(s - (int64_t)sy * a.sw);
+    const int x = sx * a.stride, y = sy * a.stride;
+    const float *p = a.rgb + 3 * ((int64_t)y * a.width + x);
+    rgb_t c{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    if (a.grid) c = bil::slice_rgb(a.grid, x, y, c, a.g, a.sigma_s, a.sigma_r, a.detail);
+    const float r = (c.x - b0) / range, g = (c.y - b0) / range, b = (c.z - b0) / range;
+    const float mask = (r >= 0.99f || g >= 0.99f || b >= 0.99f) ? 0.0f : 1.0f;
+    const float gray = r * 0.299f + g * 0.587f + b * 0.114f;
+    acc[0] += logf(fmaxf(gray, a.min_gray)) * mask;
+    acc[1] += gray * mask, acc[2] += r * mask, acc[3] += g * mask, acc[4] += b * mask, acc[5] += mask;
+  }
+  __shared__ float sh[6][kThreads / 32];
+  __shared__ unsigned int slot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) sh[k][warp] = v;
+  }
+  __syncthreads();
+  FrameState *fs = a.state;
+  if (threadIdx.x < 6) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) v += sh[threadIdx.x][w];
+    fs->partials[6 * blockIdx.x + threadIdx.x] = v;
+  }
+  if (!last_cta(&fs->ticket[1], gridDim.x, &slot)) return;
+  // fixed-order reduction of the per-CTA sums: warp k sums component k
+  if (warp < 6) {
+    float v = 0.0f;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) v += __ldcg(fs->partials + 6 * i + warp);
+    v = warp_sum(v);
+    if (lane == 0) sh[warp][0] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sums[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      sums[k] = sh[k][0] + (a.first_in_set ? 0.0f : fs->set_sums[k]);
+      fs->set_sums[k] = sums[k];
+    }
+    if (a.last_in_set) {
+      const float inv = 1.0f / fmaxf(sums[5], 1.0f);  // metrics_finalize_kernel
+      for (int k = 0; k < 5; k++) a.metrics_out[k] = ema(a.prev_metrics, k, sums[k] * inv, a.moving_average);
+    }
+    fs->ticket[1] = 0;
+  }
+}
+
+}  // namespace
+}  // namespace tdb
+
+using namespace tdb;
+
+extern "C" {
+
+int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch_buf, int width, int height, uint32_t filters, const float *ratio,
+                      const float *bounds, float eps, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && out && bounds, "frame_prepare: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0, "frame_prepare: empty image");
+  TDB_REQUIRE(!wiener_scratch_buf || eps > 0.0f, "Epsilon must be positive");
+  PrepareArgs a{rgb, out, nullptr, nullptr, nullptr, ratio, bounds, width, height, filters, eps};
+  if (wiener_scratch_buf) {
+    const WienerScratch ws = wiener_scratch(wiener_scratch_buf, width, height, 1);
+    a.loglum = ws.lum, a.zero = ws.acc, a.counters = ws.counters;
+  }
+  auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = (width % 4 == 0) && al(rgb) && al(out) && al(a.loglum) && al(a.zero);
+  const int64_t items = (int64_t)width * height / (vec ? 4 : 1);
+  if (vec) prepare_kernel<true><<<flat_grid(items), kThreads, 0, as_stream(stream)>>>(a);
+  else prepare_kernel<false><<<flat_grid(items), kThreads, 0, as_stream(stream)>>>(a);
+  return check_launch("frame_prepare");
+}
+
+int tdb_metrics_sliced(const float *rgb, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r, float detail,
+                       int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set, const float *prev_metrics,
+                       float moving_average, float *metrics_out, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && frame_state && metrics_out, "metrics_sliced: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0 && stride > 0, "metrics_sliced: bad arguments");
+  MetricsArgs a{};
+  a.rgb = rgb;
+  if (bilateral_scratch) {
+    TDB_REQUIRE(sigma_r > 0.0f && sigma_s > 0.0f, "metrics_sliced: invalid sigmas");
+    a.g = bil::grid_dims(width, height, sigma_s, sigma_r);
+    a.grid = static_cast<const float *>(bilateral_scratch) + (size_t)a.g.x * a.g.y * a.g.z;  // [splatted grid][blurred grid]
+  }
+  a.sigma_s = sigma_s, a.sigma_r = sigma_r, a.detail = detail;
+  a.width = width, a.height = height, a.stride = stride;
+  a.sw = (width + stride - 1) / stride;
+  a.nsamples = (int64_t)a.sw * ((height + stride - 1) / stride);
+  a.min_gray = min_gray;
+  a.state = static_cast<FrameState *>(frame_state);
+  a.first_in_set = first_in_set, a.last_in_set = last_in_set, a.prev_metrics = prev_metrics, a.moving_average = moving_average;
+  a.metrics_out = metrics_out;
+  metrics_sliced_kernel<<<flat_grid(a.nsamples), kThreads, 0, as_stream(stream)>>>(a);
+  return check_launch("metrics_sliced");
+}
+
+}  // extern "C"

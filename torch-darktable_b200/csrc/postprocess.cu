@@ -6,6 +6,7 @@
 // green sums are taken in the same kernel (smoothing never changes G apart from the >= 0 clamp), the ratio stays on the
 // device, and one second kernel applies the global ratio and the local equilibration: 24 B/px per kernel, no sync.
 #include "cfa_tile.cuh"
+#include "frame_state.cuh"
 
 namespace tdb {
 namespace {
@@ -17,6 +18,21 @@ struct Header {          // first bytes of the scratch buffer
   float sum1, sum2;      // G1 / G2 sums
   float ratio;           // sum2 / sum1 (or 1)
   float pad;
+};
+
+// statistics the smoothing kernel can leave behind: 1 = per-CTA green sums (the ratio kernel follows), 2 = the deferred form of
+// the fused frame pipeline: green sums AND the min / max of every stride-th pixel, kept apart for the G1 sites (which the global
+// equilibration multiplies by the ratio) and for everything else; frame_stats_kernel finishes them
+struct SmoothStats {
+  int mode;
+  int stride;
+  float *partials;
+  FrameState *state;
+  int first_in_set, last_in_set;
+  const float *prev_bounds;  // EMA state (device float[2]) or null
+  float moving_average;
+  float *bounds_out;         // device float[2], written on the last frame of a set
+  float *ratio_out;          // device float[1]
 };
 
 // ---- colour smoothing ------------------------------------------------------------------------------------------------
@@ -59,8 +75,10 @@ __device__ __forceinline__ float median_of_rows(const Triple &a, const Triple &b
 
 // 1..kMaxFusedPasses smoothing passes (+ per-CTA green sums of the result)
 __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height,
-                                                          uint32_t filters, int passes, int want_sums, float *__restrict__ partials) {
+                                                          uint32_t filters, int passes, const SmoothStats st) {
   extern __shared__ __align__(16) float sm[];
+  const int want_sums = st.mode;
+  float *__restrict__ partials = st.partials;
   const int PH = SH + 2 * passes;     // patch rows
   const int plane = PH * SPW;
   // plane order: D0r D0b X D1r D1b G.  {X, D1r, D1b} stages the raw RGB patch; the output tile takes whichever
@@ -100,6 +118,7 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
   const int cg = warp & 1, sg = warp >> 1;  // column group (2 x 32 lanes), row segment (4)
   float *outt = (passes & 1) ? xpl : d0;    // the last pass reads D[(passes-1)&1]; the tile takes the other three planes
   float s1 = 0.0f, s2 = 0.0f;
+  float lo_g = FLT_MAX, hi_g = -FLT_MAX, lo_o = FLT_MAX, hi_o = -FLT_MAX;
   const int we = width & ~1, he = height & ~1;
   // patch fully inside the image (and inside its even crop): no per-pixel tests in the passes
   const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + SPW <= we && gy0 + PH <= he;
@@ -152,19 +171,89 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
     }
     __syncthreads();
   }
+  if (want_sums == 2) {
+    // the pixels compute_image_bounds(stride) would read, straight from the finished tile (at most 5 x 8 of them)
+    const int ly0 = (st.stride - y0 % st.stride) % st.stride, lx0 = (st.stride - x0 % st.stride) % st.stride;
+    const int ny = ly0 < SH ? (SH - ly0 + st.stride - 1) / st.stride : 0, nx = lx0 < SW ? (SW - lx0 + st.stride - 1) / st.stride : 0;
+    for (int i = tid; i < ny * nx; i += kThreads) {
+      const int ly = ly0 + (i / nx) * st.stride, lx = lx0 + (i % nx) * st.stride;
+      const int gy = y0 + ly, gx = x0 + lx;
+      if (gy < height && gx < width) {
+        const float *q = outt + 3 * (ly * SW + lx);
+        const float R = q[0], G = q[1], B = q[2];
+        if ((((gx ^ gy) & 1) == green_par) && !(gy & 1)) {  // G1 site: its green takes the ratio later
+          lo_g = fminf(lo_g, G), hi_g = fmaxf(hi_g, G);
+          lo_o = fminf(lo_o, fminf(R, B)), hi_o = fmaxf(hi_o, fmaxf(R, B));
+        } else {
+          lo_o = fminf(lo_o, fminf(fminf(R, G), B)), hi_o = fmaxf(hi_o, fmaxf(fmaxf(R, G), B));
+        }
+      }
+    }
+  }
   store_rgb_tile(outt, SW * 3, out, x0, y0, SW, SH, width, height);
   if (want_sums) {
-    __shared__ float red[2][kThreads / 32];
+    __shared__ float red[6][kThreads / 32];
     s1 = warp_sum(s1), s2 = warp_sum(s2);
     if (lane == 0) red[0][warp] = s1, red[1][warp] = s2;
+    if (want_sums == 2) {
+      lo_g = warp_min(lo_g), hi_g = warp_max(hi_g), lo_o = warp_min(lo_o), hi_o = warp_max(hi_o);
+      if (lane == 0) red[2][warp] = lo_g, red[3][warp] = hi_g, red[4][warp] = lo_o, red[5][warp] = hi_o;
+    }
     __syncthreads();
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
     if (tid == 0) {
       float a = 0.0f, b = 0.0f;
 #pragma unroll
       for (int w = 0; w < kThreads / 32; w++) a += red[0][w], b += red[1][w];
-      const int blk = blockIdx.y * gridDim.x + blockIdx.x;
-      partials[2 * blk] = a, partials[2 * blk + 1] = b;
+      if (want_sums == 1) {
+        partials[2 * blk] = a, partials[2 * blk + 1] = b;
+      } else {
+        float v[4] = {FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX};
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++)
+          v[0] = fminf(v[0], red[2][w]), v[1] = fmaxf(v[1], red[3][w]), v[2] = fminf(v[2], red[4][w]), v[3] = fmaxf(v[3], red[5][w]);
+        float *p = partials + 6 * blk;
+        p[0] = a, p[1] = b, p[2] = v[0], p[3] = v[1], p[4] = v[2], p[5] = v[3];
+      }
     }
+  }
+}
+
+// Finishes the statistics of a smoothed frame from the per-CTA partials (one CTA; a ticket + __threadfence at the end of the
+// smoothing kernel itself was measured: the fence holds every CTA until its tile stores have landed, +12 % on that kernel):
+// ratio (postprocess.cu:362-366), bounds of the equilibrated image (x -> max(0, x * ratio) is monotone, so the extrema of the G1
+// class commute with it), image-set merge and moving average (image_processor.py:288-290)
+__global__ void __launch_bounds__(kThreads) frame_stats_kernel(const SmoothStats st, unsigned int nblk) {
+  __shared__ double dsum[2][kThreads / 32];
+  __shared__ float red[4][kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a = 0.0, b = 0.0;
+  float v[4] = {FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX};
+  for (unsigned int i = tid; i < nblk; i += kThreads) {
+    const float *p = st.partials + 6 * i;
+    a += p[0], b += p[1];
+    v[0] = fminf(v[0], p[2]), v[1] = fmaxf(v[1], p[3]), v[2] = fminf(v[2], p[4]), v[3] = fmaxf(v[3], p[5]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
+  v[0] = warp_min(v[0]), v[1] = warp_max(v[1]), v[2] = warp_min(v[2]), v[3] = warp_max(v[3]);
+  if (lane == 0) dsum[0][warp] = a, dsum[1][warp] = b, red[0][warp] = v[0], red[1][warp] = v[1], red[2][warp] = v[2], red[3][warp] = v[3];
+  __syncthreads();
+  if (tid == 0) {
+    a = b = 0.0;
+    for (int w = 0; w < kThreads / 32; w++) {
+      a += dsum[0][w], b += dsum[1][w];
+      v[0] = fminf(v[0], red[0][w]), v[1] = fmaxf(v[1], red[1][w]), v[2] = fminf(v[2], red[2][w]), v[3] = fmaxf(v[3], red[3][w]);
+    }
+    const float sum1 = (float)a, sum2 = (float)b;
+    const float ratio = (sum1 > 0.0f && sum2 > 0.0f) ? sum2 / sum1 : 1.0f;
+    *st.ratio_out = ratio;
+    float lo = v[2], hi = v[3];
+    if (v[0] <= v[1]) lo = fminf(lo, fmaxf(v[0] * ratio, 0.0f)), hi = fmaxf(hi, fmaxf(v[1] * ratio, 0.0f));
+    FrameState *fs = st.state;
+    if (!st.first_in_set) lo = fminf(lo, fs->set_lo), hi = fmaxf(hi, fs->set_hi);
+    fs->set_lo = lo, fs->set_hi = hi;
+    if (st.last_in_set) st.bounds_out[0] = ema(st.prev_bounds, 0, lo, st.moving_average), st.bounds_out[1] = ema(st.prev_bounds, 1, hi, st.moving_average);
   }
 }
 
@@ -277,7 +366,35 @@ extern "C" {
 
 size_t tdb_postprocess_scratch_bytes(int width, int height) {
   const size_t nblk = (size_t)div_up(width, T) * div_up(height, T);
-  return align_up(sizeof(Header), 256) + align_up(nblk * 2 * sizeof(float), 256) + 2 * (size_t)width * height * 3 * sizeof(float);
+  return align_up(sizeof(Header), 256) + align_up(nblk * 8 * sizeof(float), 256) + 2 * (size_t)width * height * 3 * sizeof(float);
+}
+
+// the smoothing chain: all passes fused in one launch when they fit (the pipeline default is 3), longer chains in chunks.
+// `final_dst` receives the last pass; `stats` applies to the last launch.  Returns the number of CTAs of that launch in *nctas.
+static int run_smoothing(const float *in, float *final_dst, float *img_a, float *img_b, int width, int height, uint32_t filters, int passes,
+                         const SmoothStats &stats, size_t *nctas, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(6 * (SH + 2 * kMaxFusedPasses) * SPW * sizeof(float)));
+    attr = true;
+  }
+  const float *cur = in;
+  int remaining = passes;
+  while (remaining > 0) {
+    const int chunk = remaining < kMaxFusedPasses ? remaining : kMaxFusedPasses;
+    const bool last = (remaining - chunk) == 0;
+    float *dst = last ? final_dst : (cur == img_a ? img_b : img_a);
+    SmoothStats st = stats;
+    if (!last) st.mode = 0;
+    dim3 sgrid(div_up(width, SW), div_up(height, SH));
+    smooth_kernel<<<sgrid, kThreads, 6 * (SH + 2 * chunk) * SPW * sizeof(float), s>>>(cur, dst, width, height, filters, chunk, st);
+    if (int e = check_launch("color_smoothing")) return e;
+    if (nctas) *nctas = (size_t)sgrid.x * sgrid.y;
+    cur = dst;
+    remaining -= chunk;
+  }
+  return TDB_OK;
 }
 
 int tdb_postprocess(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
@@ -289,33 +406,20 @@ int tdb_postprocess(const float *in, float *out, void *scratch, int width, int h
   char *base = static_cast<char *>(scratch);
   Header *hdr = reinterpret_cast<Header *>(base);
   float *partials = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256));
-  float *img_a = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256) + align_up(nblk * 2 * sizeof(float), 256));
+  float *img_a = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256) + align_up(nblk * 8 * sizeof(float), 256));
   float *img_b = img_a + (size_t)width * height * 3;
   dim3 grid(div_up(width, T), div_up(height, T));
   const bool eq = green_eq_local || green_eq_global;
 
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(6 * (SH + 2 * kMaxFusedPasses) * SPW * sizeof(float)));
-    attr = true;
-  }
   const float *cur = in;
-  int remaining = passes;
   size_t npartials = nblk;
-  // all passes fused in one launch when they fit (the pipeline default is 3); longer chains go in chunks
-  while (remaining > 0) {
-    const int chunk = remaining < kMaxFusedPasses ? remaining : kMaxFusedPasses;
-    const bool last = (remaining - chunk) == 0;
-    float *dst = (last && !eq) ? out : (cur == img_a ? img_b : img_a);
-    const int want_sums = last && green_eq_global;
-    dim3 sgrid(div_up(width, SW), div_up(height, SH));
-    smooth_kernel<<<sgrid, kThreads, 6 * (SH + 2 * chunk) * SPW * sizeof(float), s>>>(cur, dst, width, height, filters, chunk, want_sums,
-                                                                                      partials);
-    if (int e = check_launch("color_smoothing")) return e;
-    if (want_sums) npartials = (size_t)sgrid.x * sgrid.y;
-    cur = dst;
-    remaining -= chunk;
+  if (passes > 0) {
+    SmoothStats st{};
+    st.mode = green_eq_global ? 1 : 0, st.partials = partials;
+    // the last pass lands in `out` unless an equilibration pass follows (then in whichever scratch image is free)
+    float *final_dst = !eq ? out : ((((passes + kMaxFusedPasses - 1) / kMaxFusedPasses) & 1) ? img_a : img_b);
+    if (int e = run_smoothing(in, final_dst, img_a, img_b, width, height, filters, passes, st, &npartials, s)) return e;
+    cur = final_dst;
   }
   if (green_eq_global && passes == 0) {
     green_sums_kernel<<<grid, kThreads, 0, s>>>(cur, width, height, filters, partials);
@@ -335,6 +439,30 @@ int tdb_postprocess(const float *in, float *out, void *scratch, int width, int h
     check_launch("postprocess_copy");
   }
   return TDB_OK;
+}
+
+// ---- fused frame pipeline, step A: smoothing with the statistics of the (not yet applied) global green equilibration
+size_t tdb_frame_state_bytes(void) { return sizeof(FrameState); }
+
+int tdb_postprocess_deferred(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
+                             int bounds_stride, void *frame_state, int first_in_set, int last_in_set, const float *prev_bounds,
+                             float moving_average, float *bounds_out, float *ratio_out, tdb_stream_t stream) {
+  TDB_REQUIRE(in && out && scratch && frame_state && bounds_out && ratio_out, "postprocess_deferred: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0 && passes >= 1 && bounds_stride >= 1, "postprocess_deferred: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const size_t nblk = (size_t)div_up(width, T) * div_up(height, T);
+  char *base = static_cast<char *>(scratch);
+  float *partials = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256));
+  float *img_a = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256) + align_up(nblk * 8 * sizeof(float), 256));
+  float *img_b = img_a + (size_t)width * height * 3;
+  SmoothStats st{};
+  st.mode = 2, st.stride = bounds_stride, st.partials = partials, st.state = static_cast<FrameState *>(frame_state);
+  st.first_in_set = first_in_set, st.last_in_set = last_in_set, st.prev_bounds = prev_bounds, st.moving_average = moving_average;
+  st.bounds_out = bounds_out, st.ratio_out = ratio_out;
+  size_t nctas = 0;
+  if (int e = run_smoothing(in, out, img_a, img_b, width, height, filters, passes, st, &nctas, s)) return e;
+  frame_stats_kernel<<<1, kThreads, 0, s>>>(st, (unsigned int)nctas);
+  return check_launch("frame_stats");
 }
 
 // ---- pieces of the post-process for a frame that is split into row tiles across GPUs: the green sums of the rows a rank owns

@@ -7,7 +7,7 @@
 // TRANSFORMED image, so that transposing transforms still store contiguous 96-byte runs.
 // Algorithmic traffic: 12 B read + 3 B written per pixel.  The arithmetic (about 36 MUFU ops per pixel for the
 // pow/cbrt chains) rather than HBM bounds this kernel; see DESIGN.md.
-#include "color_math.cuh"
+#include "bilateral.cuh"
 
 namespace tdb {
 namespace {
@@ -20,6 +20,14 @@ struct TonemapArgs {
   const float *metrics;  // device float[5] or null
   const float *matrix;   // device float[9] or null
   int op, transform;
+};
+
+// kSlice: the pixel is produced by the bilateral slice (Bilateral.process_rgb's last step) instead of being read as is, so the
+// locally contrasted image is never written to HBM: 12 B read + 3 B written per pixel for slice + tone map together.
+struct SliceArgs {
+  const float *grid;  // blurred bilateral grid
+  bil::GridDims g;
+  float sigma_s, sigma_r, detail;
 };
 
 // destination coordinates of source pixel (x, y); (ow, oh) = transformed size.  torch.rot90(k) is counter-clockwise.
@@ -36,9 +44,9 @@ __device__ __forceinline__ void map_xy(int tf, int x, int y, int w, int h, int &
   }
 }
 
-template <int kOp>
+template <int kOp, bool kSlice>
 __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, int width,
-                                                           int height, TonemapArgs a) {
+                                                           int height, TonemapArgs a, SliceArgs sl) {
   __shared__ uint32_t tile[kTile][kTile + 1];  // 0x00BBGGRR per pixel, indexed [y][x] in SOURCE tile coordinates
 
   float m[9];
@@ -65,6 +73,7 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
     if (x < width && y < height) {
       const float *p = rgb + 3 * ((int64_t)y * width + x);
       rgb_t c{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+      if (kSlice) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
       if (has_matrix) c = mat3(m, c);
       rgb_t t;
       if (kOp == TDB_TM_ACES) {
@@ -120,22 +129,45 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
 
 using namespace tdb;
 
-extern "C" int tdb_tonemap(const float *rgb, uint8_t *out, int width, int height, int op, const float *metrics, float gamma,
-                           float intensity, float light_adapt, float vibrance, const float *matrix, int transform,
-                           tdb_stream_t stream) {
+template <bool kSlice>
+static int launch_tonemap(const float *rgb, uint8_t *out, int width, int height, const TonemapArgs &a, const SliceArgs &sl, cudaStream_t s,
+                          const char *name) {
+  dim3 grid(div_up(width, kTile), div_up(height, kTile));
+  switch (a.op) {
+    case TDB_TM_REINHARD: tonemap_kernel<TDB_TM_REINHARD, kSlice><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+    case TDB_TM_ACES: tonemap_kernel<TDB_TM_ACES, kSlice><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+    case TDB_TM_ADAPTIVE_ACES: tonemap_kernel<TDB_TM_ADAPTIVE_ACES, kSlice><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+    case TDB_TM_LINEAR: tonemap_kernel<TDB_TM_LINEAR, kSlice><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+    default: set_error("tonemap: unknown op %d", a.op); return TDB_EINVAL;
+  }
+  return check_launch(name);
+}
+
+extern "C" {
+
+int tdb_tonemap(const float *rgb, uint8_t *out, int width, int height, int op, const float *metrics, float gamma, float intensity,
+                float light_adapt, float vibrance, const float *matrix, int transform, tdb_stream_t stream) {
   TDB_REQUIRE(rgb && out, "tonemap: null pointer");
   TDB_REQUIRE(width > 0 && height > 0, "tonemap: empty image");
   TDB_REQUIRE(op == TDB_TM_ACES || metrics, "tonemap: metrics required");
   TDB_REQUIRE(transform >= TDB_TF_NONE && transform <= TDB_TF_TRANSVERSE, "tonemap: bad transform %d", transform);
   TonemapArgs a{gamma, intensity, light_adapt, vibrance, metrics, matrix, op, transform};
-  dim3 grid(div_up(width, kTile), div_up(height, kTile));
-  cudaStream_t s = as_stream(stream);
-  switch (op) {
-    case TDB_TM_REINHARD: tonemap_kernel<TDB_TM_REINHARD><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a); break;
-    case TDB_TM_ACES: tonemap_kernel<TDB_TM_ACES><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a); break;
-    case TDB_TM_ADAPTIVE_ACES: tonemap_kernel<TDB_TM_ADAPTIVE_ACES><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a); break;
-    case TDB_TM_LINEAR: tonemap_kernel<TDB_TM_LINEAR><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a); break;
-    default: set_error("tonemap: unknown op %d", op); return TDB_EINVAL;
-  }
-  return check_launch("tonemap");
+  return launch_tonemap<false>(rgb, out, width, height, a, SliceArgs{}, as_stream(stream), "tonemap");
 }
+
+int tdb_bilateral_slice_tonemap(const float *rgb, const void *bilateral_scratch, uint8_t *out, int width, int height, float sigma_s,
+                                float sigma_r, float detail, int op, const float *metrics, float gamma, float intensity,
+                                float light_adapt, float vibrance, const float *matrix, int transform, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && out && bilateral_scratch, "slice_tonemap: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0 && sigma_r > 0.0f && sigma_s > 0.0f, "slice_tonemap: invalid dimensions or sigmas");
+  TDB_REQUIRE(op == TDB_TM_ACES || metrics, "tonemap: metrics required");
+  TDB_REQUIRE(transform >= TDB_TF_NONE && transform <= TDB_TF_TRANSVERSE, "tonemap: bad transform %d", transform);
+  TonemapArgs a{gamma, intensity, light_adapt, vibrance, metrics, matrix, op, transform};
+  const bil::GridDims g = bil::grid_dims(width, height, sigma_s, sigma_r);
+  // scratch layout of bilateral.cu: [splatted grid][blurred grid]
+  const float *blurred = static_cast<const float *>(bilateral_scratch) + (size_t)g.x * g.y * g.z;
+  return launch_tonemap<true>(rgb, out, width, height, a, SliceArgs{blurred, g, sigma_s, sigma_r, detail}, as_stream(stream),
+                              "bilateral_slice_tonemap");
+}
+
+}  // extern "C"

@@ -16,8 +16,9 @@
 // No process-global device state: windows and sigmas travel as kernel arguments.
 #include <cmath>
 
-#include "color_math.cuh"
+#include "bilateral.cuh"
 #include "fft32.cuh"
+#include "wiener_layout.cuh"
 
 namespace tdb {
 namespace {
@@ -421,9 +422,14 @@ struct NormArgs {
   float *out;
   int width, height, channels, K, stride;
   float win[32];
+  // kSplat: the denoised colour is also splatted into the bilateral grid (Bilateral.process_rgb's first step), which saves the
+  // splat kernel's 12 B/px read and lets the L2 atomics overlap with the MUFU-bound Lab round trip
+  float *grid;
+  bil::GridDims g;
+  float sigma_s, sigma_r;
 };
 
-template <bool kLogLum>
+template <bool kLogLum, bool kSplat>
 __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a) {
   __shared__ float m1[32];  // 1-D mask factor per phase: sum_j win[r + j*stride]^2
   if (threadIdx.x < a.stride) {
@@ -441,6 +447,7 @@ __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a)
       const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
       const rgb_t r = pub::with_luminance(c, expf(l));
       a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
+      if (kSplat) bil::splat_pixel(a.grid, x, y, pub::luminance(r), a.g, a.sigma_s, a.sigma_r);
     } else {
       for (int ch = 0; ch < a.channels; ch++) a.out[i * a.channels + ch] = __ldg(a.acc + i * a.channels + ch) / (mask + kEps);
     }
@@ -471,7 +478,7 @@ void make_window(int K, float *win) {
 }
 
 int run_tiles(const float *in, float *acc, int width, int height, int channels, int tile, int overlap, const float *sigmas,
-              float sigma_value, cudaStream_t s) {
+              float sigma_value, cudaStream_t s, bool cleared = false) {
   WienerArgs a{};
   a.in = in, a.acc = acc, a.sigmas = sigmas, a.sigma_value = sigma_value;
   a.width = width, a.height = height, a.channels = channels;
@@ -484,8 +491,10 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   make_window(tile, a.win);
   // scratch layout: [64 floats: job counters][accumulator][extra plane]; one memset clears counters and accumulator
   a.counters = reinterpret_cast<unsigned int *>(acc) - 64;
-  cudaMemsetAsync(a.counters, 0, ((size_t)width * height * channels + 64) * sizeof(float), s);
-  check_launch("wiener_zero_accumulator");
+  if (!cleared) {
+    cudaMemsetAsync(a.counters, 0, ((size_t)width * height * channels + 64) * sizeof(float), s);
+    check_launch("wiener_zero_accumulator");
+  }
   const int sub = 32 / tile;
   const int64_t warps_needed = (a.njobs + sub - 1) / sub;
   int64_t ctas = (warps_needed + kWarps - 1) / kWarps;
@@ -574,14 +583,41 @@ int tdb_wiener(const float *in, float *out, void *scratch, int width, int height
   TDB_REQUIRE(in && out && scratch && sigmas, "Wiener: null pointer");
   if (int e = check_args(width, height, channels, tile, overlap)) return e;
   cudaStream_t s = as_stream(stream);
-  float *acc = static_cast<float *>(scratch) + 64;
+  float *acc = wiener_scratch(scratch, width, height, channels).acc;
   if (int e = run_tiles(in, acc, width, height, channels, tile, overlap, sigmas, 0.0f, s)) return e;
   NormArgs n{};
   n.acc = acc, n.rgb = nullptr, n.out = out, n.width = width, n.height = height, n.channels = channels, n.K = tile, n.stride = tile / overlap;
   make_window(tile, n.win);
   const int64_t px = (int64_t)width * height;
   const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
-  wiener_normalize_kernel<false><<<grid, 256, 0, s>>>(n);
+  wiener_normalize_kernel<false, false><<<grid, 256, 0, s>>>(n);
+  return check_launch("wiener_normalize");
+}
+
+static int run_log_luminance(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap, float noise,
+                             float eps, bool prepared, void *bilateral_scratch, float sigma_s, float sigma_r, cudaStream_t s) {
+  const WienerScratch ws = wiener_scratch(scratch, width, height, 1);
+  const int64_t px = (int64_t)width * height;
+  const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
+  if (!prepared) {
+    loglum_kernel<<<grid, 256, 0, s>>>(rgb, ws.lum, px, eps);
+    if (int e = check_launch("wiener_log_luminance")) return e;
+  }
+  NormArgs n{};
+  if (bilateral_scratch) {  // before the tiles, so that the tile kernels and the fused normalise + splat pass run back to back
+    n.g = bil::grid_dims(width, height, sigma_s, sigma_r);
+    n.grid = static_cast<float *>(bilateral_scratch), n.sigma_s = sigma_s, n.sigma_r = sigma_r;
+    if (int e = bilateral_zero_grid(bilateral_scratch, n.g, s)) return e;
+  }
+  if (int e = run_tiles(ws.lum, ws.acc, width, height, 1, tile, overlap, nullptr, noise, s, prepared)) return e;
+  n.acc = ws.acc, n.rgb = rgb, n.out = out, n.width = width, n.height = height, n.channels = 1, n.K = tile, n.stride = tile / overlap;
+  make_window(tile, n.win);
+  if (bilateral_scratch) {
+    wiener_normalize_kernel<true, true><<<grid, 256, 0, s>>>(n);
+    if (int e = check_launch("wiener_normalize_splat")) return e;
+    return bilateral_blur(bilateral_scratch, n.g, s);
+  }
+  wiener_normalize_kernel<true, false><<<grid, 256, 0, s>>>(n);
   return check_launch("wiener_normalize");
 }
 
@@ -590,19 +626,17 @@ int tdb_wiener_log_luminance(const float *rgb, float *out, void *scratch, int wi
   TDB_REQUIRE(rgb && out && scratch, "Wiener: null pointer");
   TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
   if (int e = check_args(width, height, 1, tile, overlap)) return e;
-  cudaStream_t s = as_stream(stream);
-  float *acc = static_cast<float *>(scratch) + 64;
-  float *lum = acc + (size_t)width * height;
-  const int64_t px = (int64_t)width * height;
-  const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
-  loglum_kernel<<<grid, 256, 0, s>>>(rgb, lum, px, eps);
-  if (int e = check_launch("wiener_log_luminance")) return e;
-  if (int e = run_tiles(lum, acc, width, height, 1, tile, overlap, nullptr, noise, s)) return e;
-  NormArgs n{};
-  n.acc = acc, n.rgb = rgb, n.out = out, n.width = width, n.height = height, n.channels = 1, n.K = tile, n.stride = tile / overlap;
-  make_window(tile, n.win);
-  wiener_normalize_kernel<true><<<grid, 256, 0, s>>>(n);
-  return check_launch("wiener_normalize");
+  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, false, nullptr, 0.0f, 0.0f, as_stream(stream));
+}
+
+int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap, float noise,
+                                   float eps, int prepared, void *bilateral_scratch, float sigma_s, float sigma_r, tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && out && scratch, "Wiener: null pointer");
+  TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
+  TDB_REQUIRE(!bilateral_scratch || (sigma_r > 0.0f && sigma_s > 0.0f), "Bilateral: invalid sigmas");
+  if (int e = check_args(width, height, 1, tile, overlap)) return e;
+  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, prepared != 0, bilateral_scratch, sigma_s, sigma_r,
+                           as_stream(stream));
 }
 
 }  // extern "C"

@@ -702,6 +702,85 @@ class Laplacian(_Workspace):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# fused frame pipeline (include/tdb200.h "Fused frame pipeline"; what ImageProcessor.process_image_set runs)
+class FramePipeline:
+  """Stage calls of ImageProcessor in their fused form.  Holds the device-resident statistics state of one processor; the
+  workspaces (PostProcess, Wiener, Bilateral of this module) are passed in so that their scratch buffers are shared with the
+  stage-by-stage API.  An image set is a run of frames bracketed by first / last."""
+
+  def __init__(self, device: torch.device, width: int, height: int, pattern):
+    self._device, self._width, self._height, self._filters = device, int(width), int(height), _filters(pattern)
+    self._state = torch.zeros(lib.tdb_frame_state_bytes(), dtype=torch.uint8, device=device)
+
+  def _s(self):
+    return _stream(self._device)
+
+  def smooth_deferred(self, post: 'PostProcess', rgb: torch.Tensor, first: bool, last: bool, prev_bounds: torch.Tensor | None,
+                      moving_average: float, bounds_out: torch.Tensor):
+    """Smoothing passes of `post`; the global green equilibration is deferred to `prepare`.  Returns (smoothed, ratio)."""
+    _rgb_image(rgb)
+    _require(rgb.size(0) == self._height and rgb.size(1) == self._width, 'image size mismatch')
+    out = torch.empty_like(rgb)
+    ratio = torch.empty(1, dtype=torch.float32, device=rgb.device)
+    scratch = post._ensure_scratch(lib.tdb_postprocess_scratch_bytes(self._width, self._height))
+    with torch.cuda.device(self._device):
+      check(lib.tdb_postprocess_deferred(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, self._filters,
+                                         post.color_smoothing_passes, 8, _ptr(self._state), int(first), int(last), _ptr(prev_bounds),
+                                         float(moving_average), _ptr(bounds_out), _ptr(ratio), self._s()))
+    return out, ratio
+
+  def prepare(self, rgb: torch.Tensor, ratio: torch.Tensor | None, bounds: torch.Tensor, wiener: 'Wiener | None', eps: float = 1e-4):
+    """green_eq_global (ratio) + normalize (bounds) [+ log-luminance and accumulator clear into the Wiener scratch]."""
+    _rgb_image(rgb)
+    out = torch.empty_like(rgb)
+    scratch = wiener._ensure_scratch(lib.tdb_wiener_scratch_bytes(self._width, self._height, 1, wiener._tile)) if wiener is not None else None
+    with torch.cuda.device(self._device):
+      check(lib.tdb_frame_prepare(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, self._filters, _ptr(ratio), _ptr(bounds),
+                                  float(eps), self._s()))
+    return out
+
+  def denoise(self, wiener: 'Wiener', rgb: torch.Tensor, noise: float, prepared: bool, bilateral: 'Bilateral | None', eps: float = 1e-4):
+    """Wiener.process_log_luminance; with `bilateral` the blurred grid of the result is built in its scratch on the way."""
+    _rgb_image(rgb)
+    out = torch.empty_like(rgb)
+    scratch = wiener._ensure_scratch(lib.tdb_wiener_scratch_bytes(self._width, self._height, 1, wiener._tile))
+    grid = bilateral._grid_scratch() if bilateral is not None else None
+    ss, sr = (bilateral._sigma_s, bilateral._sigma_r) if bilateral is not None else (0.0, 0.0)
+    with torch.cuda.device(self._device):
+      check(lib.tdb_wiener_log_luminance_fused(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, wiener._tile,
+                                               wiener._overlap, float(noise), float(eps), int(prepared), _ptr(grid), ss, sr, self._s()))
+    return out
+
+  def bilateral_grid(self, bilateral: 'Bilateral', rgb: torch.Tensor):
+    _rgb_image(rgb)
+    with torch.cuda.device(self._device):
+      check(lib.tdb_bilateral_grid_rgb(_ptr(rgb), _ptr(bilateral._grid_scratch()), self._width, self._height, bilateral._sigma_s,
+                                       bilateral._sigma_r, self._s()))
+
+  def metrics(self, rgb: torch.Tensor, bilateral: 'Bilateral | None', detail: float, first: bool, last: bool,
+              prev_metrics: torch.Tensor | None, moving_average: float, metrics_out: torch.Tensor, stride: int = 8, min_gray: float = 1e-4):
+    _rgb_image(rgb)
+    grid = bilateral._grid_scratch() if bilateral is not None else None
+    ss, sr = (bilateral._sigma_s, bilateral._sigma_r) if bilateral is not None else (1.0, 1.0)
+    with torch.cuda.device(self._device):
+      check(lib.tdb_metrics_sliced(_ptr(rgb), _ptr(grid), self._width, self._height, ss, sr, float(detail), int(stride), float(min_gray),
+                                   _ptr(self._state), int(first), int(last), _ptr(prev_metrics), float(moving_average), _ptr(metrics_out),
+                                   self._s()))
+
+  def slice_tonemap(self, rgb: torch.Tensor, bilateral: 'Bilateral', detail: float, op: str, metrics: torch.Tensor | None, params,
+                    matrix: torch.Tensor | None = None, transform: str = 'none') -> torch.Tensor:
+    _rgb_image(rgb)
+    h, w = self._height, self._width
+    swap = transform in ('rotate_90', 'rotate_270', 'transpose')
+    out = torch.empty((w, h, 3) if swap else (h, w, 3), dtype=torch.uint8, device=rgb.device)
+    with torch.cuda.device(self._device):
+      check(lib.tdb_bilateral_slice_tonemap(_ptr(rgb), _ptr(bilateral._grid_scratch()), _ptr(out), w, h, bilateral._sigma_s,
+                                            bilateral._sigma_r, float(detail), _TM[op], _ptr(None if op == 'aces' else metrics), params.gamma,
+                                            params.intensity, params.light_adapt, params.vibrance, _ptr(matrix), _TF[transform], self._s()))
+    return out
+
+
 def launch_count() -> int:
   """Kernels launched through libtdb200 by this process so far."""
   return _lib.launch_count()
@@ -723,7 +802,7 @@ extension = SimpleNamespace(
   bilinear5x5_demosaic=bilinear5x5_demosaic, apply_white_balance=apply_white_balance, estimate_white_balance=estimate_white_balance,
   # fused additions (not in the reference binding)
   unpack12_wb=unpack12_wb, demosaic_packed=demosaic_packed, normalize=normalize, lerp=lerp, tonemap=tonemap,
-  image_metric_sums=image_metric_sums, metrics_from_sums=metrics_from_sums, green_sums=green_sums, green_eq_apply=green_eq_apply,
+  FramePipeline=FramePipeline, image_metric_sums=image_metric_sums, metrics_from_sums=metrics_from_sums, green_sums=green_sums, green_eq_apply=green_eq_apply,
   launch_count=launch_count,
 )
 

@@ -10,6 +10,8 @@ stages run as fused libtdb200 kernels on the current CUDA stream without any hos
 
 from __future__ import annotations
 
+import os
+
 from beartype import beartype
 import torch
 
@@ -55,6 +57,8 @@ class ImageProcessor:
     self.bounds: torch.Tensor | None = None
 
     self.white_balance = (torch.tensor(white_balance, device=device).to(torch.float32) if white_balance is not None else None)
+    self._frame = extension.FramePipeline(device, image_size[0], image_size[1], bayer_pattern.value)
+    self._bil_slots: list = []
     self.wiener_workspace = td.Wiener(device, image_size)
     self.rcd_workspace = td.RCD(device, image_size, bayer_pattern)
     self._make_bilateral(settings)
@@ -63,6 +67,7 @@ class ImageProcessor:
 
   # -- workspaces -----------------------------------------------------------------------------------------------
   def _make_bilateral(self, s: ImageProcessingSettings):
+    self._bil_slots = []
     self.bil_workspace = td.Bilateral(self.device, self.image_size, sigma_s=s.bil_sigma_spatial, sigma_r=s.bil_sigma_luminance)
 
   def _make_ppg(self, s: ImageProcessingSettings):
@@ -190,6 +195,14 @@ class ImageProcessor:
 
   @beartype
   def process_image_set(self, image_set_bytes: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    if os.environ.get('TDB_UNFUSED'):
+      return self.process_image_set_by_stage(image_set_bytes)
+    return self._process_image_set_fused(image_set_bytes)
+
+  @beartype
+  def process_image_set_by_stage(self, image_set_bytes: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """The image-set composite written with the public stage calls, line by line as in the reference
+    (pipeline/image_processor.py:284-300).  `process_image_set` computes the same thing with the fused kernels."""
     names = list(image_set_bytes.keys())
     rgb_raw = [self.load_image(b) for b in image_set_bytes.values()]
 
@@ -201,3 +214,74 @@ class ImageProcessor:
     self.metrics = lerp(self.metrics if self.metrics is not None else metrics, metrics, self.settings.moving_average)
 
     return {name: self.tonemap(image, self.metrics, self._transform_for(name)) for name, image in zip(names, rgb, strict=True)}
+
+  def _state_tensor(self, t: torch.Tensor | None, n: int) -> torch.Tensor | None:
+    if t is None:
+      return None
+    assert t.numel() == n, f'expected {n} values, got {t.numel()}'
+    return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+  def _bilateral_for(self, slot: int):
+    """One grid per frame of an image set: the slice of frame i runs after the statistics of the whole set are known."""
+    while len(self._bil_slots) <= slot:
+      s = self.settings
+      self._bil_slots.append(self.bil_workspace if not self._bil_slots else
+                             td.Bilateral(self.device, self.image_size, sigma_s=s.bil_sigma_spatial, sigma_r=s.bil_sigma_luminance))
+    return self._bil_slots[slot]._bilateral
+
+  def _process_image_set_fused(self, image_set_bytes: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """Fused kernels (include/tdb200.h, "Fused frame pipeline"): per frame
+         demosaic from packed bytes -> smoothing (+ green ratio, bounds of the set, EMA)            [barrier: bounds]
+         green-eq + normalise + log-luminance -> Wiener tiles -> normalise + splat -> grid blur
+         metrics at the sampled pixels of the sliced image (+ EMA)                                  [barrier: metrics]
+         slice + tone map + transform -> uint8
+       with no host synchronisation and no statistic launch of its own."""
+    s = self.settings
+    names = list(image_set_bytes.keys())
+    n = len(names)
+    if n == 0:
+      return self.process_image_set_by_stage(image_set_bytes)
+    frame, ma = self._frame, float(s.moving_average)
+    prev_bounds, prev_metrics = self._state_tensor(self.bounds, 2), self._state_tensor(self.metrics, 5)
+
+    # -- A: load; bounds of the set
+    if s.postprocess and s.color_smoothing_passes >= 1:
+      bounds = torch.empty(2, dtype=torch.float32, device=self.device)
+      raw, ratios = [], []
+      for i, b in enumerate(image_set_bytes.values()):
+        rgb = td.demosaic_packed(self._strip(b), self.image_size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
+                                 white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
+        smoothed, ratio = frame.smooth_deferred(self.postprocess_workspace._postprocess, rgb, i == 0, i == n - 1, prev_bounds, ma, bounds)
+        raw.append(smoothed), ratios.append(ratio)
+      self.bounds = bounds
+    else:
+      raw, ratios = [self.load_image(b) for b in image_set_bytes.values()], [None] * n
+      bounds = td.compute_image_bounds(raw, stride=8)
+      self.bounds = lerp(prev_bounds if prev_bounds is not None else bounds, bounds, ma)
+
+    # -- B, C, D: per frame up to the blurred bilateral grid; metrics of the set
+    wiener = self.wiener_workspace._wiener if s.enable_denoise else None
+    metrics = torch.empty(5, dtype=torch.float32, device=self.device)
+    images = []
+    for i, (image, ratio) in enumerate(zip(raw, ratios, strict=True)):
+      bil = self._bilateral_for(i) if s.enable_bilateral else None
+      rgb = frame.prepare(image, ratio, self.bounds, wiener)
+      if wiener is not None:
+        rgb = frame.denoise(wiener, rgb, s.denoise, True, bil)
+      elif bil is not None:
+        frame.bilateral_grid(bil, rgb)
+      frame.metrics(rgb, bil, s.bilateral, i == 0, i == n - 1, prev_metrics, ma, metrics)
+      images.append(rgb)
+    self.metrics = metrics
+
+    # -- E: tone map (the bilateral slice happens inside)
+    params = td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
+    op = _TONEMAP_OPS[s.tone_mapping]
+    out = {}
+    for i, (name, rgb) in enumerate(zip(names, images, strict=True)):
+      tf = self._transform_for(name).name
+      if s.enable_bilateral:
+        out[name] = frame.slice_tonemap(rgb, self._bilateral_for(i), s.bilateral, op, self.metrics, params, None, tf)
+      else:
+        out[name] = extension.tonemap(rgb, op, None if op == 'aces' else self.metrics, params, None, tf)
+    return out
