@@ -59,9 +59,10 @@ struct TileRects {
   int start[5];          // prefix sums of the tile counts
 };
 
-__global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                       uint32_t filters, TileRects rects) {
-  extern __shared__ __align__(16) float sm[];
+// one 32 x 32 tile; `tile` = blockIdx.x of a 1-D launch over `rects`, (bx, by) = tile coordinates of a plain 2-D launch
+__device__ __forceinline__ void rcd_tile(float *sm, const CfaSource &src_in, float *__restrict__ rgb, int width, int height, uint32_t filters,
+                                         const TileRects &rects, int tile, int bx, int by) {
+  CfaSource src = src_in;
   float *cfa = sm + OFF_CFA, *vh = sm + OFF_VH, *lpf = sm + OFF_LPF, *crb = sm + OFF_CRB;
   float *vd = sm + OFF_VD, *hd = sm + OFF_HD;
   float *pd = sm + OFF_PD, *qd = sm + OFF_QD, *pq = sm + OFF_PQ, *grb = sm + OFF_GRB;
@@ -69,12 +70,11 @@ __global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__r
 
   resolve_gains(src, filters);
   const int tid = threadIdx.x;
-  int bx = blockIdx.x, by = blockIdx.y;
   if (rects.n > 0) {
     int r = 0;
 #pragma unroll
-    for (int k = 1; k < 4; k++) r += (k < rects.n && (int)blockIdx.x >= rects.start[k]) ? 1 : 0;
-    const int local = blockIdx.x - rects.start[r];
+    for (int k = 1; k < 4; k++) r += (k < rects.n && tile >= rects.start[k]) ? 1 : 0;
+    const int local = tile - rects.start[r];
     by = rects.ty0[r] + local / rects.ntx[r], bx = rects.tx0[r] + local % rects.ntx[r];
   }
   const int x0 = bx * T, y0 = by * T;
@@ -385,6 +385,12 @@ __global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__r
   store_rgb_tile(outt, T * 3, rgb, x0, y0, T, T, width, height);
 }
 
+__global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__restrict__ rgb, int width, int height, uint32_t filters,
+                                                       TileRects rects) {
+  extern __shared__ __align__(16) float sm[];
+  rcd_tile(sm, src, rgb, width, height, filters, rects, blockIdx.x, blockIdx.x, blockIdx.y);
+}
+
 
 // ======================================================================================================================
 // v2: interior tiles.  ncu of the kernel above (profiles/r01_ncu_full_v2_summary.csv): 984 thread instructions and about
@@ -447,14 +453,14 @@ __device__ __forceinline__ void stage_group(const CfaSource &s, const uint8_t *r
 
 // kG0: the CFA site (even row, even column) is green, i.e. the R/B sites of even rows sit on odd columns
 template <bool kG0>
-__global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                            uint32_t filters, int x_origin, int by_lo) {
-  extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void rcd2_tile(float *sm, const CfaSource &src_in, float *__restrict__ rgb, int width, int height, uint32_t filters,
+                                          int x_origin, int by_lo, int bx, int by) {
+  CfaSource src = src_in;
   float *cfa = sm + O_CFA, *vh = sm + O_VH, *lpf = sm + O_LPF, *crb = sm + O_CRB;
   float *vd = sm + O_VD, *hd = sm + O_HD, *pd = sm + O_PD, *qd = sm + O_QD, *pq = sm + O_PQ, *grb = sm + O_GRB;
   resolve_gains(src, filters);
   const int tid = threadIdx.x;
-  const int x0 = x_origin + blockIdx.x * TW, y0 = (blockIdx.y + by_lo) * TH;
+  const int x0 = x_origin + bx * TW, y0 = (by + by_lo) * TH;
   const int gx0 = x0 - HX, gy0 = y0 - HY;  // image coordinates of patch cell (0, 0): both even, gx0 a multiple of 4
 
   // ---- stage the CFA patch (clamped at zero like the reference's populate step)
@@ -766,6 +772,19 @@ __global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float
   }
 }
 
+// One launch for the whole image: CTAs [0, n_interior) run the 64 x 32 interior tiles, the CTAs after them the 32 x 32 tiles of
+// the frame around the interior (kernel above).  As a launch of its own the frame is latency-bound (504 CTAs at 4K, 0.046 ms next to
+// 0.203 ms for the interior); at the end of the interior grid its CTAs fill the slots that drain.
+template <bool kG0>
+__global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
+                                                            uint32_t filters, int x_origin, int by_lo, int nbx, int n_interior,
+                                                            TileRects rects) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x;
+  if (b < n_interior) rcd2_tile<kG0>(sm, src, rgb, width, height, filters, x_origin, by_lo, b % nbx, b / nbx);
+  else rcd_tile(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
+}
+
 }  // namespace v2
 }  // namespace
 
@@ -803,18 +822,14 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     for (int k = n; k < 5; k++) rects.start[k] = total;
     for (int k = n; k < 4; k++) rects.ntx[k] = 1;
     rects.n = n;
-    cudaStream_t side = s;
-    if (total > 0) {
-      side = fork_side(s);
-      rcd_kernel<<<total, kThreads, bytes, side>>>(src, rgb, width, height, filters, rects);
-      if (int e = check_launch("rcd_demosaic_frame")) return e;
-    }
-    dim3 grid2(nbx, by_hi - by_lo + 1);
-    if (fc(0, 0, filters) == 1) v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo);
-    else v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo);
-    const int e = check_launch("rcd_demosaic");
-    join_side(s, side);
-    return e;
+    static_assert(v2::SMEM_FLOATS >= SMEM_FLOATS && v2::kThreads2 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
+    const int n_interior = nbx * (by_hi - by_lo + 1);
+    const int grid2 = n_interior + total;
+    if (fc(0, 0, filters) == 1)
+      v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+    else
+      v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+    return check_launch("rcd_demosaic");
   }
   dim3 grid(ntx, nty);
   rcd_kernel<<<grid, kThreads, bytes, s>>>(src, rgb, width, height, filters, rects);

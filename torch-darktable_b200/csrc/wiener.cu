@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kThreads) wiener_tile_kernel(const WienerArgs 
 //   * transposes move (re, im) as 64-bit words: 64 + 64 shared-memory instructions instead of 128 + 128
 //   * the Hermitian pair {(ky, kx), (-ky, -kx)} shares one gain evaluation: lane ky computes both shrunk bins and
 //     hands the mirrored one to lane -ky; the 1/(2*K*K) scale is folded into the gain numerators
-template <int STRIDE, bool kBorder>
+template <int STRIDE>
 __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs a) {
   constexpr int K = 32, LD = K + 1;
   extern __shared__ float2 s_z[];  // [kWarps][K * LD] transpose staging
@@ -263,23 +263,25 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
   const int cs = a.channels;
   const int64_t row_step = (int64_t)a.width * cs;
 
-  // Interior tile pairs (both tiles inside the image) form the rectangle [px_lo, px_hi] x [gy_lo, gy_hi]: the interior
-  // instantiation enumerates exactly those and contains no reflecting code at all (half the instruction footprint:
-  // ncu showed 29 % of the stall samples waiting for instruction fetch); the border instantiation enumerates the rest.  All warps of a CTA run the same number of iterations and meet at a barrier per job, which
-  // keeps the four warps of a scheduler in the same stretch of this long, loop-free instruction stream.
-  const int64_t njobs = kBorder ? a.njobs - a.njobs_interior : a.njobs_interior;
-  unsigned int *counter = a.counters + (kBorder ? 1 : 0);
+  // Interior tile pairs (both tiles inside the image) form the rectangle [px_lo, px_hi] x [gy_lo, gy_hi]; they take a path
+  // without any reflecting code (ncu showed 29 % of the stall samples waiting for instruction fetch when every pair carried it).
+  // The job queue lists the interior pairs first and the border pairs last, so the reflecting code is only fetched while the
+  // grid drains.  kBorder is uniform per warp.  All warps of a CTA meet at a barrier per job, which keeps the four warps of a
+  // scheduler in the same stretch of this long, loop-free instruction stream.
+  const int64_t njobs = a.njobs;
+  unsigned int *counter = a.counters;
   __shared__ unsigned int s_base;
   for (;;) {
-    // dynamic scheduling: a CTA claims kWarps consecutive jobs (neighbours in x: shared lines in L1) at a time, so CTAs that
-    // start late -- the border launch runs next to the interior one on the side stream -- simply claim fewer
+    // dynamic scheduling: a CTA claims kWarps consecutive jobs (neighbours in x: shared lines in L1) at a time
     __syncthreads();
     if (threadIdx.x == 0) s_base = atomicAdd(counter, (unsigned int)kWarps);
     __syncthreads();
     const int64_t base = s_base;
     if (base >= njobs) break;
-    const int64_t job = base + warp;
+    int64_t job = base + warp;
     if (job >= njobs) continue;  // whole warps: no divergence around the shuffles
+    const bool kBorder = job >= a.njobs_interior;
+    if (kBorder) job -= a.njobs_interior;
     const int ch = (int)(job % cs);
     const int64_t t = job / cs;
     int px, gy;
@@ -510,12 +512,9 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
     static bool attr32 = false;
     if (!attr32) {
-      cudaFuncSetAttribute(wiener32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       attr32 = true;
     }
     // interior pairs: oy = (gy - shift) * stride in [0, height - 32], ox0 = (2 px - shift) * stride >= 0, ox0 + stride + 32 <= width
@@ -530,26 +529,11 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
       int64_t c = (jobs + kWarps - 1) / kWarps;  // persistent grid: two CTAs per SM
       return (int)(c > 2 * kNumSMs ? 2 * kNumSMs : (c < 1 ? 1 : c));
     };
-    cudaStream_t side = s;
-    if (a.njobs > a.njobs_interior) {  // border pairs on the side stream, next to the interior kernel
-      if (a.njobs_interior > 0) side = fork_side(s);
-      // a quarter of the CTA slots when it runs next to the interior kernel, the whole machine when it runs alone
-      const int g = side != s ? (grid_for(a.njobs - a.njobs_interior) < kNumSMs / 2 ? grid_for(a.njobs - a.njobs_interior) : kNumSMs / 2)
-                              : grid_for(a.njobs - a.njobs_interior);
-      if (st == 8) wiener32_kernel<8, true><<<g, kThreads, smem32, side>>>(a);
-      else if (st == 4) wiener32_kernel<4, true><<<g, kThreads, smem32, side>>>(a);
-      else wiener32_kernel<16, true><<<g, kThreads, smem32, side>>>(a);
-      if (int e = check_launch("wiener_tiles_border")) return e;
-    }
-    if (a.njobs_interior > 0) {
-      const int g = grid_for(a.njobs_interior);
-      if (st == 8) wiener32_kernel<8, false><<<g, kThreads, smem32, s>>>(a);
-      else if (st == 4) wiener32_kernel<4, false><<<g, kThreads, smem32, s>>>(a);
-      else wiener32_kernel<16, false><<<g, kThreads, smem32, s>>>(a);
-      if (int e = check_launch("wiener_tiles")) return e;
-    }
-    join_side(s, side);
-    return TDB_OK;
+    const int g = grid_for(a.njobs);
+    if (st == 8) wiener32_kernel<8><<<g, kThreads, smem32, s>>>(a);
+    else if (st == 4) wiener32_kernel<4><<<g, kThreads, smem32, s>>>(a);
+    else wiener32_kernel<16><<<g, kThreads, smem32, s>>>(a);
+    return check_launch("wiener_tiles");
   } else {
     wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
   }
