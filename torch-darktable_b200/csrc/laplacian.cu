@@ -3,8 +3,9 @@
 // Reference: csrc/local_contrast/laplacian.cu:446-582 = pad + input pyramid + 6 x (curve over the padded level 0 + its
 // pyramid) + assemble per level + write back: ~100 launches, 8 fp16 pyramids of the 2.5x padded frame in HBM
 // (about 190 B per image pixel at 50 MP) and pointer tables in __device__ globals.
-// Here the six tone-curved copies of level 0 are never materialised: the first reduction applies the curve while it
-// stages its fine patch in shared memory, and the level-0 assemble recomputes curve(padded) for the two gammas it
+// Here neither the padded frame nor its six tone-curved copies are ever materialised: ONE kernel builds level 1 of all seven
+// pyramids from the fp32 image (replicate padding, fp16 rounding, curves and the seven 5x5 reductions fused; CTAs over the padding
+// evaluate the curves once per distinct source pixel), and the level-0 assemble recomputes curve(image) for the two gammas it
 // blends.  The assemble passes only run on the region that can reach the cropped output, and the last one writes fp32
 // directly (write_back fused).  No global device state: level pointers travel in kernel arguments.
 // All arithmetic follows the reference's order of operations and its fp16 rounding points, so results are expected
@@ -44,9 +45,10 @@ Plan make_plan(int width, int height) {
   for (int l = 0; l < p.levels; l++) {
     p.w[l] = dl(p.bw, l), p.h[l] = dl(p.bh, l);
     const size_t n = (size_t)p.w[l] * p.h[l];
+    if (l == 0) continue;  // level 0 is virtual everywhere: the padded input and its six curved copies are recomputed from the image
     p.padded[l] = take(n);
     p.output[l] = take(n);
-    for (int k = 0; k < G; k++) p.proc[k][l] = l == 0 ? 0 : take(n);  // level 0 of the curved pyramids is virtual
+    for (int k = 0; k < G; k++) p.proc[k][l] = take(n);
   }
   p.total = off;
   return p;
@@ -68,56 +70,38 @@ __device__ __forceinline__ float curve(float x, float g, const CurveParams &cp) 
     const float t2 = t * t, mt = 1.0f - t;
     val = g + ssigma * 2.0f * mt * t + t2 * (ssigma + ssigma * shadhi);
   }
-  val += cp.clarity * c * expf(-c * c / (2.0f * cp.sigma * cp.sigma / 3.0f));
+  // clarity == 0 (the default): the term is an exact zero, skip its exp()
+  if (cp.clarity != 0.0f) val += cp.clarity * c * expf(-c * c / (2.0f * cp.sigma * cp.sigma / 3.0f));
   return val;
 }
 
 __device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
 __device__ __forceinline__ __half f2h(float f) { return __float2half_rn(f); }
 
-// replicate padding, fp32 -> fp16 (laplacian.cu:90-109)
-__global__ void __launch_bounds__(kThreads) pad_kernel(const float *__restrict__ in, __half *__restrict__ padded, int width, int height,
-                                                       int max_supp, int bw, int bh) {
-  const int x = blockIdx.x * 64 + 2 * (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= bw || y >= bh) return;
-  const int cy = min(max(y - max_supp, 0), height - 1);
-  const int cx0 = min(max(x - max_supp, 0), width - 1), cx1 = min(max(x + 1 - max_supp, 0), width - 1);
-  const float v0 = __ldg(in + (int64_t)cy * width + cx0), v1 = __ldg(in + (int64_t)cy * width + cx1);
-  __half *o = padded + (int64_t)y * bw + x;
-  if (x + 1 < bw && (((int64_t)y * bw + x) & 1) == 0) *reinterpret_cast<__half2 *>(o) = __halves2half2(f2h(v0), f2h(v1));
-  else {
-    o[0] = f2h(v0);
-    if (x + 1 < bw) o[1] = f2h(v1);
-  }
-}
-
+constexpr int NP = G + 1;  // pyramids built side by side: the six curved ones and the input's own
 struct ReduceBatch {
-  const __half *fine[G];
-  __half *coarse[G];
+  const __half *fine[NP];
+  __half *coarse[NP];
 };
 
-// 5x5 binomial, decimate by 2, clone a 1-px border (laplacian.cu:178-208).  blockIdx.z selects the pyramid.
-// kCurve: the fine level is curve_k(padded level 0), evaluated while the patch is staged (never stored in HBM).
+// 5x5 binomial, decimate by 2, clone a 1-px border (laplacian.cu:178-208), levels >= 2.  blockIdx.z selects the pyramid.
 constexpr int RT = 16;            // coarse tile edge
 constexpr int RP = 2 * RT + 3;    // fine patch edge
-template <bool kCurve>
-__global__ void __launch_bounds__(kThreads) reduce_kernel(ReduceBatch b, int cw, int ch, int fw, int fh, CurveParams cp) {
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant__ ReduceBatch b, int cw, int ch, int fw, int fh) {
   __shared__ float patch[RP][RP + 1];
   const int k = blockIdx.z;
-  const __half *__restrict__ fine = b.fine[kCurve ? 0 : k];
+  const __half *__restrict__ fine = b.fine[k];
   __half *__restrict__ coarse = b.coarse[k];
   const int cx0 = blockIdx.x * RT, cy0 = blockIdx.y * RT;
   // coarse pixel c reads fine 2*c'-2 .. 2*c'+2 with c' clamped to [1, size-2]; patch origin = 2*cx0 - 2 covers every
   // unclamped pixel of the tile, clamped border pixels are handled by reading through the same patch when possible
   const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
-  const float g = (k + 0.5f) / (float)G;
   for (int i = threadIdx.x; i < RP * RP; i += kThreads) {
     const int ly = i / RP, lx = i - ly * RP;
     const int x = fx0 + lx, y = fy0 + ly;
     float v = 0.0f;
     if (x >= 0 && y >= 0 && x < fw && y < fh) {
       v = h2f(fine[(int64_t)y * fw + x]);
-      if (kCurve) v = h2f(f2h(curve(v, g, cp)));  // the reference stores the curved level 0 as fp16
     }
     patch[ly][lx] = v;
   }
@@ -144,12 +128,87 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(ReduceBatch b, int cw,
     for (int j = -2; j <= 2; j++)
 #pragma unroll
       for (int i = -2; i <= 2; i++) {
-        float v = h2f(fine[(int64_t)(2 * cy + j) * fw + (2 * cx + i)]);
-        if (kCurve) v = h2f(f2h(curve(v, g, cp)));
-        acc += v * w[i + 2] * w[j + 2];
+        acc += h2f(fine[(int64_t)(2 * cy + j) * fw + (2 * cx + i)]) * w[i + 2] * w[j + 2];
       }
   }
   coarse[(int64_t)y * cw + x] = f2h(acc);
+}
+
+// Level 1 of all seven pyramids straight from the fp32 image: replicate padding (laplacian.cu:90-109), the fp16 rounding of the
+// padded level 0, the six curves (:266-290) and the seven 5x5 reductions (:178-208) in one pass.  The reference writes the padded
+// frame (2.5x the image at 50 MP) and six curved copies of it to HBM and reads each back; here none of them exists.
+// A CTA whose fine patch lies entirely beside / diagonally off the image sees a patch that is constant along one / both axes
+// (replicate padding): it evaluates the curves for one row / column / pixel only and lets the stencil re-read it (stride 0).
+constexpr int R1W = 32, R1H = 16;                        // coarse tile
+constexpr int P1W = 2 * R1W + 3, P1H = 2 * R1H + 3;      // fine patch 67 x 35
+constexpr int P1S = P1W + 1;
+struct Reduce1Args {
+  const float *in;  // (height, width) fp32 image
+  __half *coarse[NP];
+  int width, height, max_supp;
+  int fw, fh, cw, ch;  // padded level 0 / level 1 sizes
+};
+__global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant__ Reduce1Args a, const CurveParams cp) {
+  extern __shared__ float sm1[];  // [NP][P1H][P1S]
+  const int cx0 = blockIdx.x * R1W, cy0 = blockIdx.y * R1H;
+  const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
+  const int ms = a.max_supp;
+  // patch inside the padded frame and on one side of the image along an axis -> constant along that axis
+  const bool in_frame = fx0 >= 0 && fy0 >= 0 && fx0 + P1W <= a.fw && fy0 + P1H <= a.fh;
+  const bool flat_x = in_frame && (fx0 + P1W - 1 - ms <= 0 || fx0 - ms >= a.width - 1);
+  const bool flat_y = in_frame && (fy0 + P1H - 1 - ms <= 0 || fy0 - ms >= a.height - 1);
+  const int nx = flat_x ? 1 : P1W, ny = flat_y ? 1 : P1H;
+  for (int i = threadIdx.x; i < nx * ny; i += kThreads) {
+    const int ly = i / nx, lx = i - ly * nx;
+    const int x = fx0 + lx, y = fy0 + ly;
+    float v = 0.0f;
+    const bool inside = x >= 0 && y >= 0 && x < a.fw && y < a.fh;
+    if (inside) {
+      const int sx = min(max(x - ms, 0), a.width - 1), sy = min(max(y - ms, 0), a.height - 1);
+      v = h2f(f2h(__ldg(a.in + (int64_t)sy * a.width + sx)));
+    }
+    float *cell = sm1 + ly * P1S + lx;
+    cell[G * P1H * P1S] = v;
+#pragma unroll
+    for (int k = 0; k < G; k++) cell[k * P1H * P1S] = inside ? h2f(f2h(curve(v, (k + 0.5f) / (float)G, cp))) : 0.0f;
+  }
+  __syncthreads();
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  const int sxm = flat_x ? 0 : 1, sym = flat_y ? 0 : P1S;  // stride-0 re-reads along a constant axis
+  for (int t = threadIdx.x; t < R1W * R1H; t += kThreads) {
+    const int lx = t % R1W, ly = t / R1W;
+    const int x = cx0 + lx, y = cy0 + ly;
+    if (x >= a.cw || y >= a.ch) continue;
+    int cx = x, cy = y;
+    if (x >= a.cw - 1) cx = a.cw - 2;
+    if (y >= a.ch - 1) cy = a.ch - 2;
+    if (cx <= 0) cx = 1;
+    if (cy <= 0) cy = 1;
+    const int px = 2 * cx - fx0, py = 2 * cy - fy0;  // patch coordinates of the stencil centre
+    const bool staged = px >= 2 && py >= 2 && px + 2 < P1W && py + 2 < P1H;
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) {
+      float acc = 0.0f;
+      if (staged) {
+        const float *c = sm1 + k * P1H * P1S + py * sym + px * sxm;
+#pragma unroll
+        for (int j = -2; j <= 2; j++)
+#pragma unroll
+          for (int i = -2; i <= 2; i++) acc += c[j * sym + i * sxm] * w[i + 2] * w[j + 2];
+      } else {  // a clamped border pixel whose stencil left the staged patch (only at the far edge of the padded frame)
+#pragma unroll
+        for (int j = -2; j <= 2; j++)
+#pragma unroll
+          for (int i = -2; i <= 2; i++) {
+            const int sx = min(max(2 * cx + i - ms, 0), a.width - 1), sy = min(max(2 * cy + j - ms, 0), a.height - 1);
+            float v = h2f(f2h(__ldg(a.in + (int64_t)sy * a.width + sx)));
+            if (k < G) v = h2f(f2h(curve(v, (k + 0.5f) / (float)G, cp)));
+            acc += v * w[i + 2] * w[j + 2];
+          }
+      }
+      a.coarse[k][(int64_t)y * a.cw + x] = f2h(acc);
+    }
+  }
 }
 
 __device__ __forceinline__ float expand_gaussian(const __half *__restrict__ coarse, int px, int py, int cw) {  // :111-140
@@ -168,7 +227,8 @@ __device__ __forceinline__ float expand_gaussian(const __half *__restrict__ coar
 }
 
 struct AssembleArgs {
-  const __half *padded;      // gaussian of the input at this (fine) level
+  const __half *padded;      // gaussian of the input at this (fine) level (levels >= 1)
+  const float *image;        // level 0: the fp32 image itself (its padded fp16 copy is never stored)
   const __half *out_coarse;  // reconstruction one level coarser
   const __half *proc_fine[G];    // curved gaussians, this level (unused at level 0)
   const __half *proc_coarse[G];  // curved gaussians, one level coarser
@@ -180,7 +240,7 @@ struct AssembleArgs {
 };
 
 template <bool kLevel0>
-__global__ void __launch_bounds__(kThreads) assemble_kernel(AssembleArgs a, CurveParams cp) {  // laplacian.cu:222-263
+__global__ void __launch_bounds__(kThreads) assemble_kernel(const __grid_constant__ AssembleArgs a, CurveParams cp) {  // laplacian.cu:222-263
   const int x = a.rx0 + blockIdx.x * 32 + (threadIdx.x & 31), y = a.ry0 + blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= a.rx1 || y >= a.ry1) return;
   const int w = a.fw, h = a.fh;
@@ -191,7 +251,8 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(AssembleArgs a, Curv
   if (qy <= 0) qy = 1;
   const int cw = (w - 1) / 2 + 1;
   float val = expand_gaussian(a.out_coarse, qx, qy, cw);
-  const float v = h2f(a.padded[(int64_t)y * w + x]);
+  const float v = kLevel0 ? h2f(f2h(__ldg(a.image + (int64_t)(y - a.max_supp) * a.width + (x - a.max_supp))))
+                          : h2f(a.padded[(int64_t)y * w + x]);
   int hi = 1;
   for (; hi < G - 1 && ((float)hi + .5f) / (float)G <= v; hi++);
   const int lo = hi - 1;
@@ -233,28 +294,30 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
   const CurveParams cp{sigma, shadows, highlights, clarity};
   const int L = p.levels;
 
-  pad_kernel<<<dim3(div_up(p.bw, 64), div_up(p.bh, 8)), kThreads, 0, s>>>(lum, base + p.padded[0], width, height, p.max_supp, p.bw, p.bh);
-  if (int e = check_launch("laplacian_pad")) return e;
-
-  // gaussian pyramid of the input; the coarsest level seeds the reconstruction (laplacian.cu:515-528)
-  for (int l = 1; l < L; l++) {
-    ReduceBatch b{};
-    b.fine[0] = base + p.padded[l - 1];
-    b.coarse[0] = base + (l == L - 1 ? p.output[l] : p.padded[l]);
-    reduce_kernel<false><<<dim3(div_up(p.w[l], RT), div_up(p.h[l], RT), 1), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], cp);
-    if (int e = check_launch("laplacian_reduce")) return e;
-  }
-  // the six curved pyramids: level 1 straight from padded level 0 (curve fused), deeper levels batched over gammas
-  for (int l = 1; l < L; l++) {
-    ReduceBatch b{};
-    for (int k = 0; k < G; k++) {
-      b.fine[k] = l == 1 ? base + p.padded[0] : base + p.proc[k][l - 1];
-      b.coarse[k] = base + p.proc[k][l];
+  // level 1 of the seven pyramids from the image itself, deeper levels batched over the pyramids (blockIdx.z); the coarsest
+  // level of the input's pyramid seeds the reconstruction (laplacian.cu:515-528)
+  auto input_level = [&](int l) { return base + (l == L - 1 ? p.output[l] : p.padded[l]); };
+  {
+    static bool attr = false;
+    constexpr int bytes = NP * P1H * P1S * sizeof(float);
+    if (!attr) {
+      cudaFuncSetAttribute(reduce1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      attr = true;
     }
-    const dim3 grid(div_up(p.w[l], RT), div_up(p.h[l], RT), G);
-    if (l == 1) reduce_kernel<true><<<grid, kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], cp);
-    else reduce_kernel<false><<<grid, kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], cp);
-    if (int e = check_launch("laplacian_reduce_curves")) return e;
+    Reduce1Args r{};
+    r.in = lum, r.width = width, r.height = height, r.max_supp = p.max_supp;
+    r.fw = p.w[0], r.fh = p.h[0], r.cw = p.w[1], r.ch = p.h[1];
+    for (int k = 0; k < G; k++) r.coarse[k] = base + p.proc[k][1];
+    r.coarse[G] = input_level(1);
+    reduce1_kernel<<<dim3(div_up(p.w[1], R1W), div_up(p.h[1], R1H)), kThreads, bytes, s>>>(r, cp);
+    if (int e = check_launch("laplacian_reduce_level1")) return e;
+  }
+  for (int l = 2; l < L; l++) {
+    ReduceBatch b{};
+    for (int k = 0; k < G; k++) b.fine[k] = base + p.proc[k][l - 1], b.coarse[k] = base + p.proc[k][l];
+    b.fine[G] = input_level(l - 1), b.coarse[G] = input_level(l);
+    reduce_kernel<<<dim3(div_up(p.w[l], RT), div_up(p.h[l], RT), NP), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1]);
+    if (int e = check_launch("laplacian_reduce")) return e;
   }
   // regions of each level that can reach the cropped output: level l needs level l+1 on region/2 -+ 1
   int rx0[kMaxLevels], ry0[kMaxLevels], rx1[kMaxLevels], ry1[kMaxLevels];
@@ -266,13 +329,14 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
   }
   for (int l = L - 2; l >= 0; l--) {
     AssembleArgs a{};
-    a.padded = base + p.padded[l];
+    a.padded = l == 0 ? nullptr : base + p.padded[l];
+    a.image = lum;
     a.out_coarse = base + p.output[l + 1];
     for (int k = 0; k < G; k++) {
       a.proc_fine[k] = l == 0 ? nullptr : base + p.proc[k][l];
       a.proc_coarse[k] = base + p.proc[k][l + 1];
     }
-    a.out_fine = base + p.output[l];
+    a.out_fine = l == 0 ? nullptr : base + p.output[l];
     a.out_image = out;
     a.fw = p.w[l], a.fh = p.h[l];
     a.rx0 = rx0[l], a.ry0 = ry0[l], a.rx1 = rx1[l], a.ry1 = ry1[l];
