@@ -24,6 +24,7 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--iters', type=int, default=10)
+  ap.add_argument('--kernels', action='store_true', help='also print the per-kernel times of one call of every stage (ours only)')
   ap.add_argument('--quick', action='store_true', help='small shapes (smoke test of the script itself)')
   args = ap.parse_args()
   sys.path.insert(0, str(ROOT / ('torch-darktable_b200' if args.impl == 'ours' else 'baseline/_ref')))
@@ -59,9 +60,20 @@ def main():
                       'mp_per_s': round(mp / (ms / 1e3), 1), 'alg_bytes_per_px': bpp, 'achieved_gbs': round(gbs, 1) if gbs else None,
                       'frac_of_measured_hbm': round(gbs / peak, 4) if gbs else None, 'note': note}), flush=True)
 
+  def kernel_table(fn, inputs):
+    """per-kernel CUDA-event times of ONE call (libtdb200's timing hook; ours only)"""
+    from torch_darktable import _lib
+    torch.cuda.synchronize()
+    _lib.timing_begin(torch.cuda.current_stream(dev).cuda_stream)
+    fn(inputs[-1])
+    table = _lib.timing_end()
+    return {k: [n, round(ms, 4)] for k, (n, ms) in table.items() if k != '<begin>'}
+
   def run(config, op, w, h, bpp, fn, inputs, note=''):
     try:
       report(config, op, w, h, bpp, timeit(fn, inputs), note)
+      if ours and args.kernels:
+        print(json.dumps({'impl': args.impl, 'config': config, 'kernels_of': op, 'launches_and_ms': kernel_table(fn, inputs)}), flush=True)
     except Exception as e:  # noqa: BLE001 - one missing op must not hide the rest of the table
       print(json.dumps({'impl': args.impl, 'config': config, 'op': op, 'error': repr(e)[:300]}), flush=True)
     torch.cuda.empty_cache()

@@ -4,12 +4,12 @@
 // passes whose thread-x walks the z axis (uncoalesced) + z-derivative pass + slice; Bilateral.process_rgb adds a
 // compute_luminance pass before and a modify_luminance pass after (local_contrast.py:110-114), about 116 B/px in total.
 // Here:
-//   splat : a CTA privatises the grid cells under its 64x64 pixel tile in shared memory, then flushes one atomic per
-//           cell (about 1.2-1.6 global atomics per pixel instead of 8); the RGB variant computes Lab L on the fly;
-//   blur  : x, y (1-4-6-4-1) and the z derivative filter fused into one shared-memory pass over the grid (8 B/cell
-//           instead of 24 B/cell), thread-x along the contiguous x axis;
-//   slice : trilinear gather; the RGB variant recomputes L and applies modify_luminance in the same pass.
-// Algorithmic traffic: lum->lum 12 B/px, rgb->rgb 36 B/px, plus 2 x grid.
+//   grid  : splat and blur in ONE kernel without atomics and without the splatted grid in HBM: every grid column gathers its
+//           pixels into private bins in shared memory and the CTA filters its columns on the spot (grid_build_kernel below);
+//           the scatter with red.global.add.f32 + the separate fused blur remain for saturating grids;
+//   slice : trilinear gather; the RGB variant applies modify_luminance in the same pass and shares the Lab conversion with
+//           the luminance it needs for the lookup.
+// Algorithmic traffic: lum->lum 12 B/px, rgb->rgb 36 B/px, plus the grid once each way.
 #include "bilateral.cuh"
 
 namespace tdb {
@@ -88,6 +88,130 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(const float *__restrict_
   }
 }
 
+// ---- splat + blur without atomics ------------------------------------------------------------------------------------
+// The splat is a scatter with data-dependent z only: along x and y a pixel feeds the two cells around p / sigma_s with the hat
+// weights (1 - f, f), whatever its value.  So a grid COLUMN (i, j) can gather instead: it visits the pixels whose cell index is i - 1
+// or i (j - 1 or j), at most ceil(2 sigma_s) per axis, and adds every pixel's two z contributions into its own bins in shared
+// memory -- no atomics, no zeroed grid, and the splatted grid never exists in HBM, because the CTA gathers its 32 x 8 columns plus
+// the blur halo (36 x 12) and runs the x / y / z-derivative filter of blur_kernel on them straight away.
+// At sigma_s = 8 the atomic splat spends 1.2 ms on a 50 MP frame fighting over 64 pixels per cell; this kernel has no such term.
+// Per-pixel weights are the products of the scatter (w_x * w_y * w_z * contrib, same order); only the order of the additions
+// differs, and that order was arbitrary before (atomics) and is fixed now.
+// Not for saturating grids (more than 3000 cells per axis wanted, bilateral.cu:282-284: all pixels beyond the last cell pile up in
+// it) nor for very fine ones (sigma_s < 1); those keep the scatter.
+struct AxisSample {
+  int i;
+  float f;
+};
+__device__ __forceinline__ AxisSample axis_sample(int p, float sigma_s, int n) {  // the x / y part of make_sample
+  const float gp = fminf(fmaxf(p / sigma_s, 0.0f), (float)(n - 1));
+  const int i = min((int)gp, n - 2);
+  return AxisSample{i, gp - (float)i};
+}
+constexpr int GPX = BX + 4;  // gathered columns per CTA row (blur halo 2)
+constexpr int kMaxAxisPx = 1024;  // pixels a CTA's columns can span along one axis: (GPX + 1) * sigma_s + 4, sigma_s <= 24
+
+// kBY: grid rows per CTA (8, or 16 for shallow grids: less halo work, 1.41x instead of 1.69x gathered columns per output column)
+// kTables: fine grids (sigma_s < 3) look the per-pixel cell index / fraction up in per-CTA tables; for coarse grids neighbouring
+// columns are sigma_s pixels apart and the table reads would collide in the same banks, so they recompute them instead
+template <int kBY, bool kTables>
+__global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__restrict__ lum, float *__restrict__ out, int width, int height,
+                                                              GridDims g, float sigma_s, float sigma_r) {
+  constexpr int PY = kBY + 4;
+  extern __shared__ float sm[];
+  float *cells = sm;                     // [z][PY][GPX] splatted columns of this CTA
+  float *xb = sm + g.z * PY * GPX;       // [z][PY][BX]  after the x pass
+  // per-axis tables, built once per CTA: cell index and fraction of every pixel the CTA can touch, pixel range of every column
+  __shared__ AxisSample ax_x[kMaxAxisPx], ax_y[kMaxAxisPx];
+  __shared__ short2 rng_x[GPX], rng_y[PY];
+  const int ci0 = blockIdx.x * BX - 2, cj0 = blockIdx.y * kBY - 2;
+  const int xbase = max(0, (int)floorf((float)(ci0 - 1) * sigma_s) - 1), ybase = max(0, (int)floorf((float)(cj0 - 1) * sigma_s) - 1);
+  const int xn = min(width - xbase, min(kMaxAxisPx, (int)((GPX + 1) * sigma_s) + 8));
+  const int yn = min(height - ybase, min(kMaxAxisPx, (int)((PY + 1) * sigma_s) + 8));
+  if (kTables) {
+    for (int t = threadIdx.x; t < max(xn, yn); t += kThreads) {
+      if (t < xn) ax_x[t] = axis_sample(xbase + t, sigma_s, g.x);
+      if (t < yn) ax_y[t] = axis_sample(ybase + t, sigma_s, g.y);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < GPX + PY) {  // inclusive pixel range (relative to the base) of the pixels whose lower cell is c - 1 or c
+    const bool is_x = threadIdx.x < GPX;
+    const int c = is_x ? ci0 + threadIdx.x : cj0 + (threadIdx.x - GPX);
+    const int n = is_x ? xn : yn, base = is_x ? xbase : ybase, cells_n = is_x ? g.x : g.y;
+    auto feeds = [&](int t) {
+      const AxisSample a = axis_sample(base + t, sigma_s, cells_n);
+      return (a.i == c && a.f != 1.0f) || (a.i + 1 == c && a.f != 0.0f);
+    };
+    int lo = max(0, (int)floorf((float)(c - 1) * sigma_s) - 1 - base), hi = min(n - 1, (int)ceilf((float)(c + 1) * sigma_s) + 1 - base);
+    while (lo <= hi && !feeds(lo)) lo++;
+    while (hi >= lo && !feeds(hi)) hi--;
+    if (is_x) rng_x[threadIdx.x] = make_short2((short)lo, (short)hi);
+    else rng_y[threadIdx.x - GPX] = make_short2((short)lo, (short)hi);
+  }
+  __syncthreads();
+  const float contrib = 1.0f / (sigma_s * sigma_s);
+  // (dealing the pixel rows of a column to several threads with private bins was measured for sigma_s = 8: no gain, the coarse
+  // case is bound by its sigma_s-strided luminance loads, not by the length of the per-column chains)
+  for (int col = threadIdx.x; col < PY * GPX; col += kThreads) {
+    const int lj = col / GPX, li = col - lj * GPX;
+    const int i = ci0 + li, j = cj0 + lj;
+    float *bins = cells + lj * GPX + li;
+    for (int z = 0; z < g.z; z++) bins[z * PY * GPX] = 0.0f;
+    if (i < 0 || j < 0 || i >= g.x || j >= g.y) continue;
+    const short2 rx = rng_x[li], ry = rng_y[lj];
+    for (int ty = ry.x; ty <= ry.y; ty++) {
+      const AxisSample sy = kTables ? ax_y[ty] : axis_sample(ybase + ty, sigma_s, g.y);
+      const float wy = sy.i == j ? 1.0f - sy.f : sy.f;
+      const float *row = lum + (int64_t)(ybase + ty) * width + xbase;
+#pragma unroll 4
+      for (int tx = rx.x; tx <= rx.y; tx++) {
+        const AxisSample sx = kTables ? ax_x[tx] : axis_sample(xbase + tx, sigma_s, g.x);
+        const float wx = sx.i == i ? 1.0f - sx.f : sx.f;
+        const float gz = fminf(fmaxf(__ldg(row + tx) / sigma_r, 0.0f), (float)(g.z - 1));
+        const int iz = min((int)gz, g.z - 2);
+        const float fz = gz - (float)iz, az = 1.0f - fz;
+        const float w0 = wx * wy * az * contrib, w1 = wx * wy * fz * contrib;
+        float *b = bins + iz * PY * GPX;
+        if (w0 != 0.0f) b[0] += w0;
+        if (w1 != 0.0f) b[PY * GPX] += w1;
+      }
+    }
+  }
+  __syncthreads();
+  // x pass (cells outside the grid are zero, which is what blur_kernel's bounds tests produce)
+  const float w0 = 6.0f / 16.0f, w1 = 4.0f / 16.0f, w2 = 1.0f / 16.0f;
+  for (int t = threadIdx.x; t < g.z * PY * BX; t += kThreads) {
+    const int tx = t % BX, r = t / BX;  // r = z * PY + ly
+    const float *c = cells + r * GPX + tx + 2;
+    xb[r * BX + tx] = c[0] * w0 + w1 * (c[1] + c[-1]) + w2 * (c[2] + c[-2]);
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31;
+  const int x = blockIdx.x * BX + tx;
+  if (x >= g.x) return;
+  const int64_t plane = (int64_t)g.x * g.y;
+  const float d1 = 4.0f / 16.0f, d2 = 2.0f / 16.0f;
+  for (int ty = threadIdx.x >> 5; ty < kBY; ty += kThreads / 32) {
+    const int y = blockIdx.y * kBY + ty;
+    if (y >= g.y) break;
+    const float *b = xb + (ty + 2) * BX + tx;
+    float *o = out + (int64_t)y * g.x + x;
+    float m2 = 0.0f, m1 = 0.0f, c0 = 0.0f, p1 = 0.0f;
+    for (int z = 0; z < g.z + 2; z++, b += PY * BX) {
+      float p2 = 0.0f;
+      if (z < g.z) p2 = b[0] * w0 + w1 * (b[BX] + b[-BX]) + w2 * (b[2 * BX] + b[-2 * BX]);
+      if (z >= 2) o[plane * (z - 2)] = d1 * (p1 - m1) + d2 * (p2 - m2);
+      m2 = m1, m1 = c0, c0 = p1, p1 = p2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) luminance_plane_kernel(const float *__restrict__ rgb, float *__restrict__ lum, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    lum[i] = pub::luminance(rgb_t{__ldg(rgb + 3 * i), __ldg(rgb + 3 * i + 1), __ldg(rgb + 3 * i + 2)});
+}
+
 template <bool kRgb>
 __global__ void __launch_bounds__(kThreads) slice_kernel(const float *__restrict__ in, const float *__restrict__ grid, float *__restrict__ out,
                                                          int width, int height, GridDims g, float sigma_s, float sigma_r, float detail) {
@@ -106,19 +230,24 @@ template <bool kRgb>
 int run_bilateral(const float *in, float *out, void *scratch, int width, int height, float sigma_s, float sigma_r, float detail,
                   cudaStream_t s) {
   const GridDims g = grid_dims(width, height, sigma_s, sigma_r);
-  const size_t cells = (size_t)g.x * g.y * g.z;
-  float *grid = static_cast<float *>(scratch), *blurred = grid + cells;
-  if (int e = bilateral_zero_grid(scratch, g, s)) return e;
-  dim3 sgrid(div_up(width, TP), div_up(height, TP));
-  splat_kernel<kRgb><<<sgrid, kThreads, 0, s>>>(in, grid, width, height, g, sigma_s, sigma_r);
-  if (int e = check_launch("bilateral_splat")) return e;
-  if (int e = bilateral_blur(scratch, g, s)) return e;
+  const float *lum = in;
+  if (kRgb) {
+    float *plane = bilateral_lum_plane(scratch, g);
+    const int64_t n = (int64_t)width * height;
+    luminance_plane_kernel<<<(int)((n + kThreads - 1) / kThreads < kNumSMs * 16 ? (n + kThreads - 1) / kThreads : kNumSMs * 16), kThreads, 0, s>>>(in, plane, n);
+    if (int e = check_launch("bilateral_luminance")) return e;
+    lum = plane;
+  }
+  if (int e = bilateral_build_grid(scratch, lum, width, height, g, sigma_s, sigma_r, s)) return e;
   dim3 pgrid(div_up(width, 32), div_up(height, 8));
-  slice_kernel<kRgb><<<pgrid, kThreads, 0, s>>>(in, blurred, out, width, height, g, sigma_s, sigma_r, detail);
+  slice_kernel<kRgb><<<pgrid, kThreads, 0, s>>>(in, bilateral_blurred(scratch, g), out, width, height, g, sigma_s, sigma_r, detail);
   return check_launch("bilateral_slice");
 }
 
 }  // namespace
+
+float *bilateral_lum_plane(void *scratch, bil::GridDims g) { return static_cast<float *>(scratch) + 2 * (size_t)g.x * g.y * g.z; }
+const float *bilateral_blurred(const void *scratch, bil::GridDims g) { return static_cast<const float *>(scratch) + (size_t)g.x * g.y * g.z; }
 
 int bilateral_zero_grid(void *scratch, bil::GridDims g, cudaStream_t s) {
   cudaMemsetAsync(scratch, 0, (size_t)g.x * g.y * g.z * sizeof(float), s);
@@ -139,6 +268,37 @@ int bilateral_blur(void *scratch, bil::GridDims g, cudaStream_t s) {
   return check_launch("bilateral_blur");
 }
 
+// splatted + blurred grid of a luminance plane, into the second half of the grid scratch
+int bilateral_build_grid(void *scratch, const float *lum, int width, int height, bil::GridDims g, float sigma_s, float sigma_r,
+                         cudaStream_t s) {
+  // the gather needs every pixel to feed the two cells around p / sigma_s: no saturation at the last cell (grid_dims clamps
+  // the cell count to 3000 per axis), and a bounded number of pixels per cell
+  const bool gather = sigma_s >= 1.0f && (width - 1) / sigma_s <= (float)(g.x - 1) && (height - 1) / sigma_s <= (float)(g.y - 1) &&
+                      (GPX + 1) * sigma_s + 8.0f <= (float)kMaxAxisPx;
+  if (gather) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(grid_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 20 * (GPX + BX) * 4);
+      attr = true;
+    }
+    float *blurred = static_cast<float *>(scratch) + (size_t)g.x * g.y * g.z;
+    if (g.z <= 16 && sigma_s < 3.0f) {
+      grid_build_kernel<16, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * 20 * (GPX + BX) * sizeof(float), s>>>(
+          lum, blurred, width, height, g, sigma_s, sigma_r);
+    } else {
+      grid_build_kernel<8, false><<<dim3(div_up(g.x, BX), div_up(g.y, 8)), kThreads, (size_t)g.z * 12 * (GPX + BX) * sizeof(float), s>>>(
+          lum, blurred, width, height, g, sigma_s, sigma_r);
+    }
+    return check_launch("bilateral_grid_build");
+  }
+  if (int e = bilateral_zero_grid(scratch, g, s)) return e;
+  dim3 sgrid(div_up(width, TP), div_up(height, TP));
+  splat_kernel<false><<<sgrid, kThreads, 0, s>>>(lum, static_cast<float *>(scratch), width, height, g, sigma_s, sigma_r);
+  if (int e = check_launch("bilateral_splat")) return e;
+  return bilateral_blur(scratch, g, s);
+}
+
 }  // namespace tdb
 
 using namespace tdb;
@@ -155,7 +315,7 @@ int tdb_bilateral_grid_size(int width, int height, float sigma_s, float sigma_r,
 size_t tdb_bilateral_scratch_bytes(int width, int height, float sigma_s, float sigma_r) {
   if (width <= 0 || height <= 0 || !(sigma_s > 0.0f) || !(sigma_r > 0.0f)) return 0;
   const GridDims g = grid_dims(width, height, sigma_s, sigma_r);
-  return 2 * (size_t)g.x * g.y * g.z * sizeof(float);
+  return (2 * (size_t)g.x * g.y * g.z + (size_t)width * height) * sizeof(float);  // two grids + a luminance plane
 }
 
 int tdb_bilateral(const float *lum, float *out, void *scratch, int width, int height, float sigma_s, float sigma_r, float detail,
@@ -177,11 +337,11 @@ int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int heigh
   TDB_REQUIRE(width > 0 && height > 0 && sigma_r > 0.0f && sigma_s > 0.0f, "Bilateral: invalid dimensions or sigmas");
   cudaStream_t s = as_stream(stream);
   const bil::GridDims g = bil::grid_dims(width, height, sigma_s, sigma_r);
-  if (int e = bilateral_zero_grid(scratch, g, s)) return e;
-  dim3 sgrid(div_up(width, TP), div_up(height, TP));
-  splat_kernel<true><<<sgrid, kThreads, 0, s>>>(rgb, static_cast<float *>(scratch), width, height, g, sigma_s, sigma_r);
-  if (int e = check_launch("bilateral_splat")) return e;
-  return bilateral_blur(scratch, g, s);
+  float *plane = bilateral_lum_plane(scratch, g);
+  const int64_t n = (int64_t)width * height;
+  luminance_plane_kernel<<<(int)((n + kThreads - 1) / kThreads < kNumSMs * 16 ? (n + kThreads - 1) / kThreads : kNumSMs * 16), kThreads, 0, s>>>(rgb, plane, n);
+  if (int e = check_launch("bilateral_luminance")) return e;
+  return bilateral_build_grid(scratch, plane, width, height, g, sigma_s, sigma_r, s);
 }
 
 }  // extern "C"

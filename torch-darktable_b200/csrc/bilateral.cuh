@@ -99,8 +99,12 @@ __device__ __forceinline__ void splat_pixel(float *__restrict__ grid, int x, int
 
 }  // namespace bil
 
-// host-side pieces of bilateral.cu used by the fused frame pipeline (scratch = [splat grid][blurred grid])
+// host-side pieces of bilateral.cu used by the fused frame pipeline (scratch = [splat grid][blurred grid][luminance plane])
+float *bilateral_lum_plane(void *scratch, bil::GridDims g);
+const float *bilateral_blurred(const void *scratch, bil::GridDims g);
 int bilateral_zero_grid(void *scratch, bil::GridDims g, cudaStream_t s);
 int bilateral_blur(void *scratch, bil::GridDims g, cudaStream_t s);
+int bilateral_build_grid(void *scratch, const float *lum, int width, int height, bil::GridDims g, float sigma_s, float sigma_r,
+                         cudaStream_t s);
 
 }  // namespace tdb

@@ -175,8 +175,12 @@ __global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant
   __syncthreads();
   const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
   const int sxm = flat_x ? 0 : 1, sym = flat_y ? 0 : P1S;  // stride-0 re-reads along a constant axis
-  for (int t = threadIdx.x; t < R1W * R1H; t += kThreads) {
-    const int lx = t % R1W, ly = t / R1W;
+  // a patch that is constant along an axis gives results that are constant along it too: one column / row / pixel of the tile is
+  // computed and the stores replicate it (flat tiles lie inside the frame, where no coarse coordinate is clamped)
+  const int ncx = flat_x ? 1 : R1W, ncy = flat_y ? 1 : R1H;
+  __shared__ __half res[NP][R1H][R1W];
+  for (int t = threadIdx.x; t < ncx * ncy; t += kThreads) {
+    const int lx = t % ncx, ly = t / ncx;
     const int x = cx0 + lx, y = cy0 + ly;
     if (x >= a.cw || y >= a.ch) continue;
     int cx = x, cy = y;
@@ -206,7 +210,21 @@ __global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant
             acc += v * w[i + 2] * w[j + 2];
           }
       }
-      a.coarse[k][(int64_t)y * a.cw + x] = f2h(acc);
+      res[k][ly][lx] = f2h(acc);
+    }
+  }
+  __syncthreads();
+  // stores: half2 along x (cw is even only sometimes: pair up when the row offset is even)
+  for (int t = threadIdx.x; t < NP * R1H * (R1W / 2); t += kThreads) {
+    const int lx = 2 * (t % (R1W / 2)), ly = (t / (R1W / 2)) % R1H, k = t / (R1H * (R1W / 2));
+    const int x = cx0 + lx, y = cy0 + ly;
+    if (x >= a.cw || y >= a.ch) continue;
+    const __half v0 = res[k][flat_y ? 0 : ly][flat_x ? 0 : lx], v1 = res[k][flat_y ? 0 : ly][flat_x ? 0 : lx + 1];
+    __half *o = a.coarse[k] + (int64_t)y * a.cw + x;
+    if (x + 1 < a.cw && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) *reinterpret_cast<__half2 *>(o) = __halves2half2(v0, v1);
+    else {
+      o[0] = v0;
+      if (x + 1 < a.cw) o[1] = v1;
     }
   }
 }

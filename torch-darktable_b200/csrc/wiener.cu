@@ -424,11 +424,9 @@ struct NormArgs {
   float *out;
   int width, height, channels, K, stride;
   float win[32];
-  // kSplat: the denoised colour is also splatted into the bilateral grid (Bilateral.process_rgb's first step), which saves the
-  // splat kernel's 12 B/px read and lets the L2 atomics overlap with the MUFU-bound Lab round trip
-  float *grid;
-  bil::GridDims g;
-  float sigma_s, sigma_r;
+  // kSplat: the Lab L of the denoised colour is stored as well (4 B/px): it is what the bilateral grid is built from
+  // (Bilateral.process_rgb's first step), so that stage does not read the image again
+  float *lum_out;
 };
 
 template <bool kLogLum, bool kSplat>
@@ -449,7 +447,7 @@ __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a)
       const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
       const rgb_t r = pub::with_luminance(c, expf(l));
       a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
-      if (kSplat) bil::splat_pixel(a.grid, x, y, pub::luminance(r), a.g, a.sigma_s, a.sigma_r);
+      if (kSplat) a.lum_out[i] = pub::luminance(r);
     } else {
       for (int ch = 0; ch < a.channels; ch++) a.out[i * a.channels + ch] = __ldg(a.acc + i * a.channels + ch) / (mask + kEps);
     }
@@ -588,18 +586,18 @@ static int run_log_luminance(const float *rgb, float *out, void *scratch, int wi
     if (int e = check_launch("wiener_log_luminance")) return e;
   }
   NormArgs n{};
-  if (bilateral_scratch) {  // before the tiles, so that the tile kernels and the fused normalise + splat pass run back to back
-    n.g = bil::grid_dims(width, height, sigma_s, sigma_r);
-    n.grid = static_cast<float *>(bilateral_scratch), n.sigma_s = sigma_s, n.sigma_r = sigma_r;
-    if (int e = bilateral_zero_grid(bilateral_scratch, n.g, s)) return e;
+  bil::GridDims g{};
+  if (bilateral_scratch) {
+    g = bil::grid_dims(width, height, sigma_s, sigma_r);
+    n.lum_out = bilateral_lum_plane(bilateral_scratch, g);
   }
   if (int e = run_tiles(ws.lum, ws.acc, width, height, 1, tile, overlap, nullptr, noise, s, prepared)) return e;
   n.acc = ws.acc, n.rgb = rgb, n.out = out, n.width = width, n.height = height, n.channels = 1, n.K = tile, n.stride = tile / overlap;
   make_window(tile, n.win);
   if (bilateral_scratch) {
     wiener_normalize_kernel<true, true><<<grid, 256, 0, s>>>(n);
-    if (int e = check_launch("wiener_normalize_splat")) return e;
-    return bilateral_blur(bilateral_scratch, n.g, s);
+    if (int e = check_launch("wiener_normalize_lum")) return e;
+    return bilateral_build_grid(bilateral_scratch, n.lum_out, width, height, g, sigma_s, sigma_r, s);
   }
   wiener_normalize_kernel<true, false><<<grid, 256, 0, s>>>(n);
   return check_launch("wiener_normalize");
