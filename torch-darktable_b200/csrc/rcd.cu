@@ -12,7 +12,10 @@
 // positions (or zero).  `stale_cell` reproduces exactly that for a FRESH reference workspace, so the output matches a
 // freshly constructed reference RCD object everywhere, including the band just inside the 7-px margin.  What the
 // reference leaks from the PREVIOUS frame (rows 2-3 of VH_dir) is deliberately not reproduced.
+#include <cstdlib>
+
 #include "cfa_tile.cuh"
+#include "rcd_planar.cuh"
 
 namespace tdb {
 namespace {
@@ -786,6 +789,17 @@ __global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float
 }
 
 }  // namespace v2
+
+// v3 interior tiles (rcd_planar.cuh) + the frame tiles of the kernel above in one launch, as for v2
+template <bool kG0>
+__global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
+                                                                uint32_t filters, int x_origin, int by_lo, int nbx, int n_interior,
+                                                                TileRects rects) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x;
+  if (b < n_interior) v3::rcd3_tile<kG0>(sm, src, rgb, width, height, filters, x_origin, by_lo, b % nbx, b / nbx);
+  else rcd_tile(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
+}
 }  // namespace
 
 int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, cudaStream_t s) {
@@ -804,7 +818,7 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
   const int nbx = (width - x_origin - (v2::TW + v2::HX)) / v2::TW + 1;   // x_origin + 64 bx + 76 <= width
   const int by_lo = 1, by_hi = (height - (v2::TH + v2::HY)) / v2::TH;    // 32 by + 44 <= height
   const bool aligned = (width % 4 == 0) && (reinterpret_cast<uintptr_t>(rgb) % 16 == 0) &&
-                       (src.cfa ? reinterpret_cast<uintptr_t>(src.cfa) % 8 == 0
+                       (src.cfa ? reinterpret_cast<uintptr_t>(src.cfa) % 16 == 0
                                 : (reinterpret_cast<uintptr_t>(src.packed) % 4 == 0 && ((int64_t)width * height * 3 / 2) % 4 == 0));
   TileRects rects{};
   const int ntx = div_up(width, T), nty = div_up(height, T);
@@ -823,8 +837,25 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     for (int k = n; k < 4; k++) rects.ntx[k] = 1;
     rects.n = n;
     static_assert(v2::SMEM_FLOATS >= SMEM_FLOATS && v2::kThreads2 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
+    static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads && v3::TW == v2::TW && v3::TH == v2::TH && v3::HX == v2::HX &&
+                  v3::HY == v2::HY, "v3 tiles the image like v2");
     const int n_interior = nbx * (by_hi - by_lo + 1);
     const int grid2 = n_interior + total;
+    static const bool use_v2 = getenv("TDB_RCD_V2") != nullptr;  // A/B switch: the row-major shared-memory layout
+    if (!use_v2) {
+      constexpr size_t bytes3 = v3::SMEM_FLOATS * sizeof(float);
+      static bool attr3 = false;
+      if (!attr3) {
+        cudaFuncSetAttribute(rcd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
+        cudaFuncSetAttribute(rcd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
+        attr3 = true;
+      }
+      if (fc(0, 0, filters) == 1)
+        rcd3_kernel<true><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      else
+        rcd3_kernel<false><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      return check_launch("rcd_demosaic");
+    }
     if (fc(0, 0, filters) == 1)
       v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
     else
