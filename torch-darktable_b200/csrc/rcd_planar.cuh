@@ -29,7 +29,7 @@ constexpr int O_CFA = 0, O_VH = FULL, O_LPF = 2 * FULL, O_CRB = O_LPF + HALF, O_
 constexpr int O_VD = O_U, O_HD = O_U + FULL;                                                   // phase 1
 constexpr int O_PD = O_U, O_QD = O_U + HALF, O_PQ = O_U + 2 * HALF, O_GRB = O_U + 3 * HALF;    // later phases
 constexpr int SMEM_FLOATS = O_U + 4 * HALF;
-constexpr int kThreads3 = 256;
+constexpr int kThreads3 = 256;  // (512 threads per CTA = 32 warps per SM was measured: no faster, and the frame tiles need a launch of their own)
 static_assert(4 * HALF >= 2 * FULL, "union region");
 static_assert((2 * RS) % 32 == 20 && (2 * RH) % 32 == 20 && 4 * PQ <= RS && 2 * PQ <= RH, "bank plan");
 
