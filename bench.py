@@ -209,8 +209,14 @@ def run_ours(args):
                    'share': round(total_ms / sum(v[1] for v in table.values()), 4), 'alg_bytes_per_px': bpp,
                    'achieved_gbs': round(gbs, 1) if gbs else None, 'frac': round(gbs / peak, 4) if gbs else None})
   top = stages[0]
+  traffic = None  # dram__bytes_read + dram__bytes_write of the dominant kernel per launch, from the committed ncu --set full capture
+  try:
+    t = json.loads((ROOT / 'profiles' / 'ncu_traffic.json').read_text())['kernels'].get(top['kernel'])
+    traffic = (t['dram_read_bytes'] + t['dram_write_bytes']) if t else None
+  except (OSError, ValueError, KeyError):
+    pass
   roofline = {'kernel': top['kernel'], 'bound': 'hbm', 'achieved': top['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-              'frac': top['frac'], 'traffic': None, 'peak_source': peak_src, 'ms_per_launch': top['ms_per_launch'],
+              'frac': top['frac'], 'traffic': traffic, 'peak_source': peak_src, 'ms_per_launch': top['ms_per_launch'],
               'note': 'wiener_tiles is FP32-issue bound (register FFTs, 16 covering tiles per pixel), not HBM bound; see DESIGN.md'}
 
   # end to end through host buffers

@@ -103,3 +103,55 @@ def test_bayer_helpers_roundtrip():
     cfa = td.rgb_to_bayer(rgb, p)
     assert cfa.shape == (8, 12, 1)
     assert torch.equal(td.bayer.expand_bayer(td.bayer.stack_bayer(cfa[..., 0])), cfa)
+
+
+def test_raw_ingest_finds_the_camera_by_directory_then_by_size(tmp_path):
+  """pipeline/camera_settings.py:55-132 of the reference: headerless packed files, camera from the directory name or the byte count."""
+  import numpy as np
+  import torch
+  from torch_darktable.pipeline.camera_settings import (load_camera_settings_from_dir, load_raw_bytes, load_raw_bytes_stripped,
+                                                        settings_for_file)
+  known = load_camera_settings_from_dir()
+  cam = known['artichoke']
+  (tmp_path / 'artichoke').mkdir()
+  by_dir = tmp_path / 'artichoke' / 'frame0.raw'
+  by_dir.write_bytes(b'\x00' * 10)
+  assert settings_for_file(by_dir).name == 'artichoke'
+  (tmp_path / 'unknown').mkdir()
+  by_size = tmp_path / 'unknown' / 'frame1.raw'
+  payload = np.random.default_rng(3).integers(0, 256, cam.bytes, dtype=np.uint8)
+  by_size.write_bytes(payload.tobytes())
+  found = settings_for_file(by_size)
+  assert found.bytes == cam.bytes
+  raw = load_raw_bytes(by_size, torch.device('cpu'))
+  assert raw.dtype == torch.uint8 and np.array_equal(raw.numpy(), payload)
+  stripped = load_raw_bytes_stripped(by_size, found, torch.device('cpu'))
+  assert stripped.numel() == found.bytes - found.padding
+  bad = tmp_path / 'unknown' / 'frame2.raw'
+  bad.write_bytes(b'\x00' * 12345)
+  with pytest.raises(ValueError, match='Could not find camera settings'):
+    settings_for_file(bad)
+
+
+def test_estimate_channel_noise_matches_a_numpy_restatement():
+  """denoise.py:131-158 of the reference: 4-neighbour Laplacian, every stride-th response, MAD / 0.6745 per channel (device-agnostic
+  torch code in both packages; checked on the CPU against plain numpy, and against the sigma it is meant to recover)."""
+  import numpy as np
+  import torch
+  import torch_darktable as td
+  rng = np.random.default_rng(11)
+  sig = np.array([0.01, 0.02, 0.04], np.float32)
+  img = (0.5 + rng.normal(0.0, 1.0, (160, 200, 3)) * sig).astype(np.float32)
+  got = td.estimate_channel_noise(torch.from_numpy(img), stride=4).numpy()
+  pad = np.pad(img, ((1, 1), (1, 1), (0, 0)))
+  resp = 4 * pad[1:-1, 1:-1] - pad[:-2, 1:-1] - pad[2:, 1:-1] - pad[1:-1, :-2] - pad[1:-1, 2:]
+  resp = resp[::4, ::4].reshape(-1, 3)
+
+  def lower_median(a):  # torch.median returns the lower of the two middle values
+    return np.sort(a, axis=0)[(a.shape[0] - 1) // 2]
+
+  med = lower_median(resp)
+  want = lower_median(np.abs(resp - med)) / 0.6745
+  np.testing.assert_allclose(got, want, rtol=1e-4)
+  # the Laplacian of white noise has sigma * sqrt(20): the estimate scales with the true sigma
+  np.testing.assert_allclose(got / np.sqrt(20.0), sig, rtol=0.15)

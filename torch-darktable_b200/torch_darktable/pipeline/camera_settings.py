@@ -52,8 +52,12 @@ class CameraSettings(BaseModel, frozen=True):
 
 @beartype
 def load_raw_bytes(filepath: Path, device: torch.device = torch.device('cuda:0')):
-  """File contents as a uint8 device tensor, undecoded."""
-  return torch.frombuffer(filepath.read_bytes(), dtype=torch.uint8).to(device, non_blocking=True)
+  """File contents as a uint8 device tensor, undecoded: read straight into pinned host memory, then one asynchronous copy on the
+  current stream (the pinned block is recycled by torch's host allocator once that copy has run)."""
+  host = torch.empty(filepath.stat().st_size, dtype=torch.uint8, pin_memory=device.type == 'cuda')
+  with open(filepath, 'rb') as f:
+    f.readinto(host.numpy())
+  return host.to(device, non_blocking=True)
 
 
 @beartype
