@@ -44,26 +44,88 @@ __device__ __forceinline__ void map_xy(int tf, int x, int y, int w, int h, int &
   }
 }
 
+// per-launch constants of the tone curve (reference color_adaption.h:17-44)
+struct ToneConsts {
+  float m[9];
+  bool has_matrix;
+  float map_key, exposure, mean[3], aces_gain, inv_gamma, light_adapt, vibrance;
+};
+template <int kOp>
+__device__ __forceinline__ ToneConsts tone_consts(const TonemapArgs &a) {
+  ToneConsts k{};
+  k.has_matrix = a.matrix != nullptr;
+  if (k.has_matrix) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) k.m[i] = __ldg(a.matrix + i);
+  }
+  k.map_key = 0.0f, k.exposure = 1.0f;
+  if (kOp != TDB_TM_ACES) {
+    const float normalized = fmaxf(0.0f, fminf(1.0f, (-__ldg(a.metrics)) / 9.21034f));
+    k.map_key = 0.3f + 0.7f * powf(normalized, 1.4f);
+    k.exposure = expf(a.intensity);
+    k.mean[0] = __ldg(a.metrics + 2), k.mean[1] = __ldg(a.metrics + 3), k.mean[2] = __ldg(a.metrics + 4);
+  }
+  k.aces_gain = powf(2.0f, a.intensity);
+  k.inv_gamma = 1.0f / a.gamma;
+  k.light_adapt = a.light_adapt, k.vibrance = a.vibrance;
+  return k;
+}
+// one pixel: [slice] -> [3x3] -> tone curve -> gamma -> vibrance -> 0x00BBGGRR
+template <int kOp, bool kSlice>
+__device__ __forceinline__ uint32_t tone_pixel(rgb_t c, int x, int y, const ToneConsts &k, const SliceArgs &sl) {
+  if (kSlice) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
+  if (k.has_matrix) c = mat3(k.m, c);
+  rgb_t t;
+  if (kOp == TDB_TM_ACES) {
+    t = tm::aces_fit(rgb_t{c.x * k.aces_gain, c.y * k.aces_gain, c.z * k.aces_gain});
+  } else {
+    // lerp(light_adapt, global_mean, pixel) / exposure, to the power map_key  (color_adaption.h:46-76)
+    const float ax = powf((k.mean[0] + k.light_adapt * (c.x - k.mean[0])) / k.exposure, k.map_key);
+    const float ay = powf((k.mean[1] + k.light_adapt * (c.y - k.mean[1])) / k.exposure, k.map_key);
+    const float az = powf((k.mean[2] + k.light_adapt * (c.z - k.mean[2])) / k.exposure, k.map_key);
+    if (kOp == TDB_TM_REINHARD) t = rgb_t{c.x / (ax + c.x), c.y / (ay + c.y), c.z / (az + c.z)};
+    else if (kOp == TDB_TM_LINEAR) t = rgb_t{c.x / ax, c.y / ay, c.z / az};
+    else t = tm::aces_fit(rgb_t{c.x / ax, c.y / ay, c.z / az});
+  }
+  const rgb_t g{powf(fmaxf(t.x, 0.0f), k.inv_gamma), powf(fmaxf(t.y, 0.0f), k.inv_gamma), powf(fmaxf(t.z, 0.0f), k.inv_gamma)};
+  const rgb_t v = tm::vibrance(g, k.vibrance);
+  return tm::to_u8(v.x) | (tm::to_u8(v.y) << 8) | (tm::to_u8(v.z) << 16);
+}
+
+// Transforms that keep rows as rows (none, flips, rotate_180): a thread owns four consecutive pixels of a row -- three 128-bit
+// loads, three 32-bit stores of the twelve result bytes -- and no shared-memory tile is needed.  width % 4 == 0.
+template <int kOp, bool kSlice>
+__global__ void __launch_bounds__(kThreads) tonemap_rows_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, int width,
+                                                                int height, TonemapArgs a, SliceArgs sl) {
+  const ToneConsts k = tone_consts<kOp>(a);
+  const bool flip_x = a.transform == TDB_TF_FLIP_HORIZ || a.transform == TDB_TF_ROTATE_180 || a.transform == TDB_TF_TRANSVERSE;
+  const bool flip_y = a.transform == TDB_TF_FLIP_VERT || a.transform == TDB_TF_ROTATE_180 || a.transform == TDB_TF_TRANSVERSE;
+  const int wq = width >> 2;
+  const int64_t ngroups = (int64_t)wq * height;
+  for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * kThreads) {
+    const int y = (int)(g / wq), x = 4 * (int)(g - (int64_t)y * wq);
+    const float4 *src = reinterpret_cast<const float4 *>(rgb) + 3 * g;
+    rgb_t p[4];
+    unpack4(__ldg(src), __ldg(src + 1), __ldg(src + 2), p);
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = tone_pixel<kOp, kSlice>(p[i], x + i, y, k, sl);
+    if (flip_x) {
+      const uint32_t t0 = v[0], t1 = v[1];
+      v[0] = v[3], v[1] = v[2], v[2] = t1, v[3] = t0;
+    }
+    const int oy = flip_y ? height - 1 - y : y, ox = flip_x ? width - 4 - x : x;
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + 3 * ((int64_t)oy * width + ox));  // 12-byte groups of a 4-byte aligned buffer
+    o[0] = v[0] | (v[1] << 24), o[1] = (v[1] >> 8) | (v[2] << 16), o[2] = (v[2] >> 16) | (v[3] << 8);
+  }
+}
+
 template <int kOp, bool kSlice>
 __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, int width,
                                                            int height, TonemapArgs a, SliceArgs sl) {
   __shared__ uint32_t tile[kTile][kTile + 1];  // 0x00BBGGRR per pixel, indexed [y][x] in SOURCE tile coordinates
 
-  float m[9];
-  const bool has_matrix = a.matrix != nullptr;
-  if (has_matrix) {
-#pragma unroll
-    for (int i = 0; i < 9; i++) m[i] = __ldg(a.matrix + i);
-  }
-  float map_key = 0.0f, exposure = 1.0f, mean[3] = {0, 0, 0};
-  if (kOp != TDB_TM_ACES) {  // reference color_adaption.h:17-44
-    const float normalized = fmaxf(0.0f, fminf(1.0f, (-__ldg(a.metrics)) / 9.21034f));
-    map_key = 0.3f + 0.7f * powf(normalized, 1.4f);
-    exposure = expf(a.intensity);
-    mean[0] = __ldg(a.metrics + 2), mean[1] = __ldg(a.metrics + 3), mean[2] = __ldg(a.metrics + 4);
-  }
-  const float aces_gain = powf(2.0f, a.intensity);
-  const float inv_gamma = 1.0f / a.gamma;
+  const ToneConsts kc = tone_consts<kOp>(a);
 
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
   const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
@@ -72,24 +134,7 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
     const int ly = ly0 + 8 * k, x = x0 + lx, y = y0 + ly;
     if (x < width && y < height) {
       const float *p = rgb + 3 * ((int64_t)y * width + x);
-      rgb_t c{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-      if (kSlice) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
-      if (has_matrix) c = mat3(m, c);
-      rgb_t t;
-      if (kOp == TDB_TM_ACES) {
-        t = tm::aces_fit(rgb_t{c.x * aces_gain, c.y * aces_gain, c.z * aces_gain});
-      } else {
-        // lerp(light_adapt, global_mean, pixel) / exposure, to the power map_key  (color_adaption.h:46-76)
-        const float ax = powf((mean[0] + a.light_adapt * (c.x - mean[0])) / exposure, map_key);
-        const float ay = powf((mean[1] + a.light_adapt * (c.y - mean[1])) / exposure, map_key);
-        const float az = powf((mean[2] + a.light_adapt * (c.z - mean[2])) / exposure, map_key);
-        if (kOp == TDB_TM_REINHARD) t = rgb_t{c.x / (ax + c.x), c.y / (ay + c.y), c.z / (az + c.z)};
-        else if (kOp == TDB_TM_LINEAR) t = rgb_t{c.x / ax, c.y / ay, c.z / az};
-        else t = tm::aces_fit(rgb_t{c.x / ax, c.y / ay, c.z / az});
-      }
-      const rgb_t g{powf(fmaxf(t.x, 0.0f), inv_gamma), powf(fmaxf(t.y, 0.0f), inv_gamma), powf(fmaxf(t.z, 0.0f), inv_gamma)};
-      const rgb_t v = tm::vibrance(g, a.vibrance);
-      tile[ly][lx] = tm::to_u8(v.x) | (tm::to_u8(v.y) << 8) | (tm::to_u8(v.z) << 16);
+      tile[ly][lx] = tone_pixel<kOp, kSlice>(rgb_t{__ldg(p), __ldg(p + 1), __ldg(p + 2)}, x, y, kc, sl);
     }
   }
   __syncthreads();
@@ -132,6 +177,20 @@ using namespace tdb;
 template <bool kSlice>
 static int launch_tonemap(const float *rgb, uint8_t *out, int width, int height, const TonemapArgs &a, const SliceArgs &sl, cudaStream_t s,
                           const char *name) {
+  const bool rows = a.transform == TDB_TF_NONE || a.transform == TDB_TF_FLIP_HORIZ || a.transform == TDB_TF_FLIP_VERT ||
+                    a.transform == TDB_TF_ROTATE_180 || a.transform == TDB_TF_TRANSVERSE;
+  if (rows && width % 4 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    const int64_t groups = (int64_t)(width / 4) * height;
+    const int g1 = (int)((groups + kThreads - 1) / kThreads < (int64_t)kNumSMs * 16 ? (groups + kThreads - 1) / kThreads : kNumSMs * 16);
+    switch (a.op) {
+      case TDB_TM_REINHARD: tonemap_rows_kernel<TDB_TM_REINHARD, kSlice><<<g1, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+      case TDB_TM_ACES: tonemap_rows_kernel<TDB_TM_ACES, kSlice><<<g1, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+      case TDB_TM_ADAPTIVE_ACES: tonemap_rows_kernel<TDB_TM_ADAPTIVE_ACES, kSlice><<<g1, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+      case TDB_TM_LINEAR: tonemap_rows_kernel<TDB_TM_LINEAR, kSlice><<<g1, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
+      default: set_error("tonemap: unknown op %d", a.op); return TDB_EINVAL;
+    }
+    return check_launch(name);
+  }
   dim3 grid(div_up(width, kTile), div_up(height, kTile));
   switch (a.op) {
     case TDB_TM_REINHARD: tonemap_kernel<TDB_TM_REINHARD, kSlice><<<grid, kThreads, 0, s>>>(rgb, out, width, height, a, sl); break;
