@@ -120,7 +120,11 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
   constexpr int PY = kBY + 4;
   extern __shared__ float sm[];
   float *cells = sm;                     // [z][PY][GPX] splatted columns of this CTA
-  float *xb = sm + g.z * PY * GPX;       // [z][PY][BX]  after the x pass
+  // plane stride of the bins: a multiple of 32 words, so that the bank of a bin depends on the column only -- the lanes of a warp own
+  // consecutive columns but hit different z planes (data dependent), and with the natural stride (720 = 16 mod 32) lanes whose
+  // z differ by an odd number collided
+  constexpr int ZS = (PY * GPX + 31) / 32 * 32;
+  float *xb = sm + g.z * ZS;             // [z][PY][BX]  after the x pass
   // per-axis tables, built once per CTA: cell index and fraction of every pixel the CTA can touch, pixel range of every column
   __shared__ AxisSample ax_x[kMaxAxisPx], ax_y[kMaxAxisPx];
   __shared__ short2 rng_x[GPX], rng_y[PY];
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
     const int lj = col / GPX, li = col - lj * GPX;
     const int i = ci0 + li, j = cj0 + lj;
     float *bins = cells + lj * GPX + li;
-    for (int z = 0; z < g.z; z++) bins[z * PY * GPX] = 0.0f;
+    for (int z = 0; z < g.z; z++) bins[z * ZS] = 0.0f;
     if (i < 0 || j < 0 || i >= g.x || j >= g.y) continue;
     const short2 rx = rng_x[li], ry = rng_y[lj];
     for (int ty = ry.x; ty <= ry.y; ty++) {
@@ -172,9 +176,9 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
         const int iz = min((int)gz, g.z - 2);
         const float fz = gz - (float)iz, az = 1.0f - fz;
         const float w0 = wx * wy * az * contrib, w1 = wx * wy * fz * contrib;
-        float *b = bins + iz * PY * GPX;
+        float *b = bins + iz * ZS;
         if (w0 != 0.0f) b[0] += w0;
-        if (w1 != 0.0f) b[PY * GPX] += w1;
+        if (w1 != 0.0f) b[ZS] += w1;
       }
     }
   }
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
   const float w0 = 6.0f / 16.0f, w1 = 4.0f / 16.0f, w2 = 1.0f / 16.0f;
   for (int t = threadIdx.x; t < g.z * PY * BX; t += kThreads) {
     const int tx = t % BX, r = t / BX;  // r = z * PY + ly
-    const float *c = cells + r * GPX + tx + 2;
+    const float *c = cells + (r / PY) * ZS + (r % PY) * GPX + tx + 2;
     xb[r * BX + tx] = c[0] * w0 + w1 * (c[1] + c[-1]) + w2 * (c[2] + c[-2]);
   }
   __syncthreads();
@@ -279,15 +283,15 @@ int bilateral_build_grid(void *scratch, const float *lum, int width, int height,
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(grid_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 20 * (GPX + BX) * 4);
+      cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
       attr = true;
     }
     float *blurred = static_cast<float *>(scratch) + (size_t)g.x * g.y * g.z;
     if (g.z <= 16 && sigma_s < 3.0f) {
-      grid_build_kernel<16, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * 20 * (GPX + BX) * sizeof(float), s>>>(
+      grid_build_kernel<16, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(
           lum, blurred, width, height, g, sigma_s, sigma_r);
     } else {
-      grid_build_kernel<8, false><<<dim3(div_up(g.x, BX), div_up(g.y, 8)), kThreads, (size_t)g.z * 12 * (GPX + BX) * sizeof(float), s>>>(
+      grid_build_kernel<8, false><<<dim3(div_up(g.x, BX), div_up(g.y, 8)), kThreads, (size_t)g.z * (((12 * GPX + 31) / 32 * 32) + 12 * BX) * sizeof(float), s>>>(
           lum, blurred, width, height, g, sigma_s, sigma_r);
     }
     return check_launch("bilateral_grid_build");

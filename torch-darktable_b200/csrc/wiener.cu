@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(kThreads) wiener_tile_kernel(const WienerArgs 
 //   * transposes move (re, im) as 64-bit words: 64 + 64 shared-memory instructions instead of 128 + 128
 //   * the Hermitian pair {(ky, kx), (-ky, -kx)} shares one gain evaluation: lane ky computes both shrunk bins and
 //     hands the mirrored one to lane -ky; the 1/(2*K*K) scale is folded into the gain numerators
-template <int STRIDE>
+// kC1: single-channel image (the log-luminance path of the pipeline): the second tile of a pair sits at an immediate offset
+template <int STRIDE, bool kC1>
 __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs a) {
   constexpr int K = 32, LD = K + 1;
   extern __shared__ float2 s_z[];  // [kWarps][K * LD] transpose staging
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
   const float wc = a.win[lane];
   const int partner = (K - lane) & (K - 1);  // lane holding -ky
   constexpr int shift = K / STRIDE;          // the tile grid starts one tile early (denoise.cu:146)
-  const int cs = a.channels;
+  const int cs = kC1 ? 1 : a.channels;
   const int64_t row_step = (int64_t)a.width * cs;
 
   // Interior tile pairs (both tiles inside the image) form the rectangle [px_lo, px_hi] x [gy_lo, gy_hi]; they take a path
@@ -314,12 +315,15 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
     float re[K], im[K];
     float sum_a = 0.0f, sum_b = 0.0f;
     if (!kBorder) {
-      const float *p = a.in + ((int64_t)oy * a.width + ox0 + lane) * cs + ch;
-      const int boff = STRIDE * cs;
+      // 32-bit element offsets from the plane base (check_args: they fit): one IMAD.WIDE per row instead of the 64-bit pointer
+      // walks the compiler made of `p += row_step` (8 integer instructions per row, ncu)
+      int off = (int)(((int64_t)oy * a.width + ox0 + lane) * cs + ch);
+      const int boff = kC1 ? STRIDE : STRIDE * cs, rs = (int)row_step;
 #pragma unroll
       for (int r = 0; r < K; r++) {
+        const float *p = a.in + off;
         re[r] = __ldg(p), im[r] = __ldg(p + boff);
-        p += row_step;
+        off += rs;
       }
     } else {
       const int xa = reflect_index(ox0 + lane, a.width), xb = reflect_index(ox1 + lane, a.width);
@@ -393,14 +397,15 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
 
     // overlap-add: (value + mean * w_fft) * w_interp   (store_pixel, denoise.cu:150-178)
     if (!kBorder) {
-      float *o = a.acc + ((int64_t)oy * a.width + ox0 + lane) * cs + ch;
-      const int boff = STRIDE * cs;
+      int off = (int)(((int64_t)oy * a.width + ox0 + lane) * cs + ch);
+      const int boff = kC1 ? STRIDE : STRIDE * cs, rs = (int)row_step;
 #pragma unroll
       for (int r = 0; r < K; r++) {
         const float w = a.win[r] * wc;
+        float *o = a.acc + off;
         atomicAdd(o, fmaf(mean_a, w, re[r]) * w);
         atomicAdd(o + boff, fmaf(mean_b, w, im[r]) * w);
-        o += row_step;
+        off += rs;
       }
     } else {
       const int xa = ox0 + lane, xb = ox1 + lane;
@@ -510,9 +515,12 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
     static bool attr32 = false;
     if (!attr32) {
-      cudaFuncSetAttribute(wiener32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      cudaFuncSetAttribute(wiener32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+      cudaFuncSetAttribute(wiener32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       attr32 = true;
     }
     // interior pairs: oy = (gy - shift) * stride in [0, height - 32], ox0 = (2 px - shift) * stride >= 0, ox0 + stride + 32 <= width
@@ -528,9 +536,15 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
       return (int)(c > 2 * kNumSMs ? 2 * kNumSMs : (c < 1 ? 1 : c));
     };
     const int g = grid_for(a.njobs);
-    if (st == 8) wiener32_kernel<8><<<g, kThreads, smem32, s>>>(a);
-    else if (st == 4) wiener32_kernel<4><<<g, kThreads, smem32, s>>>(a);
-    else wiener32_kernel<16><<<g, kThreads, smem32, s>>>(a);
+    if (channels == 1) {
+      if (st == 8) wiener32_kernel<8, true><<<g, kThreads, smem32, s>>>(a);
+      else if (st == 4) wiener32_kernel<4, true><<<g, kThreads, smem32, s>>>(a);
+      else wiener32_kernel<16, true><<<g, kThreads, smem32, s>>>(a);
+    } else {
+      if (st == 8) wiener32_kernel<8, false><<<g, kThreads, smem32, s>>>(a);
+      else if (st == 4) wiener32_kernel<4, false><<<g, kThreads, smem32, s>>>(a);
+      else wiener32_kernel<16, false><<<g, kThreads, smem32, s>>>(a);
+    }
     return check_launch("wiener_tiles");
   } else {
     wiener_tile_kernel<16><<<(int)ctas, kThreads, smem, s>>>(a);
@@ -540,6 +554,7 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
 
 int check_args(int width, int height, int channels, int tile, int overlap) {
   if (width <= 0 || height <= 0) { set_error("Wiener: image dimensions must be positive"); return TDB_EINVAL; }
+  if ((int64_t)width * height * channels >= (int64_t)1 << 31) { set_error("Wiener: image too large (2^31 samples)"); return TDB_EINVAL; }
   if (channels != 1 && channels != 3) { set_error("input channels must be 1 or 3, got %d", channels); return TDB_EINVAL; }
   if (tile != 16 && tile != 32) { set_error("tile_size must be 16 or 32, got %d", tile); return TDB_EINVAL; }
   if (overlap != 2 && overlap != 4 && overlap != 8) { set_error("overlap_factor must be 2, 4, or 8"); return TDB_EINVAL; }
