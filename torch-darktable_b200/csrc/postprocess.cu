@@ -73,14 +73,67 @@ __device__ __forceinline__ float median_of_rows(const Triple &a, const Triple &b
   return med3(max3(a.lo, b.lo, c.lo), med3(a.mid, b.mid, c.mid), min3(a.hi, b.hi, c.hi));
 }
 
-// 1..kMaxFusedPasses smoothing passes (+ per-CTA green sums of the result)
+// One column segment of one pass: the thread walks down rows [rb, re) of its column.  Everything that does not change inside the
+// walk is a template argument or an immediate: the plane stride (kPlane), whether the pass is the last one (writes the RGB tile
+// and the green sums instead of the difference planes) and whether the patch lies inside the image (no per-pixel tests).  The row
+// loop is unrolled by three with the sorted row triples renamed instead of moved; v2 of this loop spent more instructions on
+// register rotation, five pointer walks and per-pixel predicates (IMAD 94, ISETP 31, VIADD 25, FSEL 16 per output pixel) than on
+// the min/max network itself (143).
+template <int kPasses, bool kLast, bool kInside>
+__device__ __forceinline__ void smooth_rows(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ gpl,
+                                            float *__restrict__ outt, int rb, int re, int col, int gx, int gy0, int width, int height,
+                                            int we, int he, bool green_row0, int want_sums, float &s1, float &s2) {
+  constexpr int kPlane = (SH + 2 * kPasses) * SPW;
+  const bool col_in = gx >= 0 && gx < width;
+  const float *p = src + (rb - 1) * SPW + col;
+  Triple ra = sort3(p[-1], p[0], p[1]), ba = sort3(p[kPlane - 1], p[kPlane], p[kPlane + 1]);
+  Triple rm = sort3(p[SPW - 1], p[SPW], p[SPW + 1]), bm = sort3(p[kPlane + SPW - 1], p[kPlane + SPW], p[kPlane + SPW + 1]);
+  Triple rc, bc;
+  p += 2 * SPW;                    // row rb + 1: the row below the first output
+  float *pg = gpl + rb * SPW + col, *pd = dst + rb * SPW + col;
+  float *po = outt + 3 * ((rb - kPasses) * SW + (col - SHX));
+  // one output row: T2 = sorted triples of the row below (loaded here), T0 / T1 = the two rows above
+#define TDB_SMOOTH_ROW(K, R0, B0, R1, B1, R2, B2)                                                                   \
+  {                                                                                                                 \
+    R2 = sort3(p[(K) * SPW - 1], p[(K) * SPW], p[(K) * SPW + 1]);                                                   \
+    B2 = sort3(p[kPlane + (K) * SPW - 1], p[kPlane + (K) * SPW], p[kPlane + (K) * SPW + 1]);                        \
+    const float mr = median_of_rows(R0, R1, R2), mb = median_of_rows(B0, B1, B2);                                   \
+    const float g = pg[(K) * SPW];                                                                                  \
+    float R = fmaxf(mr + g, 0.0f), B = fmaxf(mb + g, 0.0f), G = fmaxf(g, 0.0f);                                     \
+    const int gy = gy0 + r + (K);                                                                                   \
+    const bool pix_in = kInside || (col_in && gy >= 0 && gy < height);                                              \
+    if (!kInside && !pix_in) R = 0.0f, G = 0.0f, B = 0.0f; /* outside stays zero for the next pass */               \
+    if (!kLast) {                                                                                                   \
+      pd[(K) * SPW] = R - G, pd[kPlane + (K) * SPW] = B - G;                                                        \
+      pg[(K) * SPW] = G;                                                                                            \
+    } else {                                                                                                        \
+      po[(K) * 3 * SW] = R, po[(K) * 3 * SW + 1] = G, po[(K) * 3 * SW + 2] = B;                                     \
+      if (want_sums) { /* green sums over the even-cropped image (postprocess.cu:195-203) */                        \
+        const bool green = green_row0 != (bool)((r + (K)) & 1);                                                     \
+        const bool counted = green && (kInside || (pix_in && gx < we && gy < he));                                  \
+        const float gs = counted ? G : 0.0f;                                                                        \
+        if (gy & 1) s2 += gs; else s1 += gs;                                                                        \
+      }                                                                                                             \
+    }                                                                                                               \
+  }
+  for (int r = rb; r < re; r += 3, p += 3 * SPW, pg += 3 * SPW, pd += 3 * SPW, po += 9 * SW) {
+    TDB_SMOOTH_ROW(0, ra, ba, rm, bm, rc, bc)
+    if (r + 1 < re) TDB_SMOOTH_ROW(1, rm, bm, rc, bc, ra, ba)
+    if (r + 2 < re) TDB_SMOOTH_ROW(2, rc, bc, ra, ba, rm, bm)
+  }
+#undef TDB_SMOOTH_ROW
+}
+
+// kPasses = 1..kMaxFusedPasses smoothing passes (+ per-CTA green sums of the result)
+template <int kPasses>
 __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restrict__ in, float *__restrict__ out, int width, int height,
-                                                          uint32_t filters, int passes, const SmoothStats st) {
+                                                          uint32_t filters, const SmoothStats st) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int passes = kPasses;
   const int want_sums = st.mode;
   float *__restrict__ partials = st.partials;
-  const int PH = SH + 2 * passes;     // patch rows
-  const int plane = PH * SPW;
+  constexpr int PH = SH + 2 * passes;     // patch rows
+  constexpr int plane = PH * SPW;
   // plane order: D0r D0b X D1r D1b G.  {X, D1r, D1b} stages the raw RGB patch; the output tile takes whichever
   // three contiguous planes the last pass does not read
   float *d0 = sm, *xpl = sm + 2 * plane, *d1 = sm + 3 * plane, *gpl = sm + 5 * plane;
@@ -123,10 +176,10 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
   // patch fully inside the image (and inside its even crop): no per-pixel tests in the passes
   const bool inside = gx0 >= 0 && gy0 >= 0 && gx0 + SPW <= we && gy0 + PH <= he;
   const int green_par = fc(0, 0, filters) == 1 ? 0 : 1;  // green sites: (x + y) & 1 == green_par
+#pragma unroll
   for (int m = 1; m <= passes; m++) {
     const float *src = ((m - 1) & 1) ? d1 : d0;
     float *dst = (m & 1) ? d1 : d0;
-    const bool last = m == passes;
     const int grow = passes - m;  // how far beyond the output tile this pass must still be valid
     const int r_lo = passes - grow, r_hi = passes + SH + grow;  // rows [r_lo, r_hi)
     const int c_lo = SHX - grow, c_hi = SHX + SW + grow;
@@ -135,38 +188,13 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
     const int col = c_lo + cg * 32 + lane;
     if (col < c_hi && rb < re) {
       const int gx = gx0 + col;
-      const bool col_in = gx >= 0 && gx < width;
-      const float *pr = src + (rb - 1) * SPW + col, *pb = pr + plane;
-      Triple ra = sort3(pr[-1], pr[0], pr[1]), ba = sort3(pb[-1], pb[0], pb[1]);
-      pr += SPW, pb += SPW;
-      Triple rbt = sort3(pr[-1], pr[0], pr[1]), bbt = sort3(pb[-1], pb[0], pb[1]);
-      float *pg = gpl + rb * SPW + col;
-      float *pd = dst + rb * SPW + col;
-      float *po = outt + 3 * ((rb - passes) * SW + (col - SHX));
       const bool green_row0 = ((gx ^ gy0) & 1) == green_par;  // is (gx, patch row 0) a green site
-      for (int r = rb; r < re; r++, pg += SPW, pd += SPW, po += 3 * SW) {
-        pr += SPW, pb += SPW;
-        const Triple rc = sort3(pr[-1], pr[0], pr[1]), bc = sort3(pb[-1], pb[0], pb[1]);
-        const float mr = median_of_rows(ra, rbt, rc), mb = median_of_rows(ba, bbt, bc);
-        const float g = *pg;
-        float R = fmaxf(mr + g, 0.0f), B = fmaxf(mb + g, 0.0f), G = fmaxf(g, 0.0f);
-        const int gy = gy0 + r;
-        const bool pix_in = inside || (col_in && gy >= 0 && gy < height);
-        if (!pix_in) R = 0.0f, G = 0.0f, B = 0.0f;  // outside stays zero for the next pass
-        if (!last) {
-          pd[0] = R - G, pd[plane] = B - G;
-          *pg = G;
-        } else {
-          po[0] = R, po[1] = G, po[2] = B;
-          // green sums over the even-cropped image (postprocess.cu:195-203)
-          if (want_sums) {
-            const bool green = green_row0 != (bool)(r & 1);
-            const bool counted = green && (inside || (pix_in && gx < we && gy < he));
-            const float gs = counted ? G : 0.0f;
-            if (gy & 1) s2 += gs; else s1 += gs;
-          }
-        }
-        ra = rbt, rbt = rc, ba = bbt, bbt = bc;
+      if (m < passes) {
+        if (inside) smooth_rows<kPasses, false, true>(src, dst, gpl, outt, rb, re, col, gx, gy0, width, height, we, he, green_row0, 0, s1, s2);
+        else smooth_rows<kPasses, false, false>(src, dst, gpl, outt, rb, re, col, gx, gy0, width, height, we, he, green_row0, 0, s1, s2);
+      } else {
+        if (inside) smooth_rows<kPasses, true, true>(src, dst, gpl, outt, rb, re, col, gx, gy0, width, height, we, he, green_row0, want_sums, s1, s2);
+        else smooth_rows<kPasses, true, false>(src, dst, gpl, outt, rb, re, col, gx, gy0, width, height, we, he, green_row0, want_sums, s1, s2);
       }
     }
     __syncthreads();
@@ -375,8 +403,10 @@ static int run_smoothing(const float *in, float *final_dst, float *img_a, float 
                          const SmoothStats &stats, size_t *nctas, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(6 * (SH + 2 * kMaxFusedPasses) * SPW * sizeof(float)));
+    cudaFuncSetAttribute(smooth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 1) * SPW * sizeof(float)));
+    cudaFuncSetAttribute(smooth_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 2) * SPW * sizeof(float)));
+    cudaFuncSetAttribute(smooth_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 3) * SPW * sizeof(float)));
+    cudaFuncSetAttribute(smooth_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 4) * SPW * sizeof(float)));
     attr = true;
   }
   const float *cur = in;
@@ -388,7 +418,13 @@ static int run_smoothing(const float *in, float *final_dst, float *img_a, float 
     SmoothStats st = stats;
     if (!last) st.mode = 0;
     dim3 sgrid(div_up(width, SW), div_up(height, SH));
-    smooth_kernel<<<sgrid, kThreads, 6 * (SH + 2 * chunk) * SPW * sizeof(float), s>>>(cur, dst, width, height, filters, chunk, st);
+    const size_t bytes = 6 * (SH + 2 * chunk) * SPW * sizeof(float);
+    switch (chunk) {
+      case 1: smooth_kernel<1><<<sgrid, kThreads, bytes, s>>>(cur, dst, width, height, filters, st); break;
+      case 2: smooth_kernel<2><<<sgrid, kThreads, bytes, s>>>(cur, dst, width, height, filters, st); break;
+      case 3: smooth_kernel<3><<<sgrid, kThreads, bytes, s>>>(cur, dst, width, height, filters, st); break;
+      default: smooth_kernel<4><<<sgrid, kThreads, bytes, s>>>(cur, dst, width, height, filters, st); break;
+    }
     if (int e = check_launch("color_smoothing")) return e;
     if (nctas) *nctas = (size_t)sgrid.x * sgrid.y;
     cur = dst;
