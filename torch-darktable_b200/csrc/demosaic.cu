@@ -94,7 +94,96 @@ __global__ void __launch_bounds__(kThreads) bilinear_kernel(CfaSource src, float
 //   med  : optional thresholded 9-tap same-colour median, halo 4                     (ppg.cu:21-113)
 //   tmp  : per-pixel RGB after border_interpolate(3) / green fill, halo 1            (ppg.cu:342-389, :120-223)
 //   out  : red/blue fill from tmp                                                    (ppg.cu:230-337)
-template <bool kMedian>
+// One pixel of the `tmp` stage the slow way: outside the image, or in the 3-px ring that border_interpolate owns (ppg.cu:342-389)
+__device__ __forceinline__ void ppg_tmp_border(const float *cfa_px, int sc, int x, int y, int width, int height, uint32_t filters, float *t) {
+  float r = 0.0f, g = 0.0f, b = 0.0f;  // zero outside the image (ppg.cu:270)
+  if (x >= 0 && y >= 0 && x < width && y < height) {
+    const int c = fc(y, x, filters);
+    // 3x3 same-colour averages of the RAW cfa clamped at 0
+    float sum[3] = {0, 0, 0};
+    int cnt[3] = {0, 0, 0};
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++) {
+        const int xx = x + dx, yy = y + dy;
+        if (xx >= 0 && yy >= 0 && xx < width && yy < height) {
+          const int f = fc(yy, xx, filters);
+          const float v = fmaxf(0.0f, cfa_px[dy * sc + dx]);
+          sum[0] += f == 0 ? v : 0.0f, sum[1] += f == 1 ? v : 0.0f, sum[2] += f == 2 ? v : 0.0f;
+          cnt[0] += f == 0, cnt[1] += f == 1, cnt[2] += f == 2;
+        }
+      }
+    const float v = fmaxf(0.0f, cfa_px[0]);
+    r = cnt[0] > 0 ? sum[0] / cnt[0] : v;
+    g = cnt[1] > 0 ? sum[1] / cnt[1] : v;
+    b = cnt[2] > 0 ? sum[2] / cnt[2] : v;
+    if (c == 0) r = v; else if (c == 2) b = v; else g = v;
+  }
+  t[0] = r, t[1] = g, t[2] = b;
+}
+
+// One interior pixel of the `tmp` stage: the native sample, and PPG green at R / B sites (ppg.cu:120-223).
+// kType: 0 = R site, 1 = G on an R row, 2 = G on a B row, 3 = B site (compile time: a thread owns a whole 2x2 quad)
+template <int kType>
+__device__ __forceinline__ void ppg_tmp_pixel(const float *p, int gs, float *t) {
+  const float pc = p[0];
+  float r = 0.0f, g = 0.0f, b = 0.0f;
+  if (kType == 0) r = pc; else if (kType == 3) b = pc; else g = pc;
+  if (kType == 0 || kType == 3) {
+    const float pym = p[-gs], pym2 = p[-2 * gs], pym3 = p[-3 * gs];
+    const float pyM = p[gs], pyM2 = p[2 * gs], pyM3 = p[3 * gs];
+    const float pxm = p[-1], pxm2 = p[-2], pxm3 = p[-3], pxM = p[1], pxM2 = p[2], pxM3 = p[3];
+    const float guessx = (pxm + pc + pxM) * 2.0f - pxM2 - pxm2;
+    const float diffx = (fabsf(pxm2 - pc) + fabsf(pxM2 - pc) + fabsf(pxm - pxM)) * 3.0f + (fabsf(pxM3 - pxM) + fabsf(pxm3 - pxm)) * 2.0f;
+    const float guessy = (pym + pc + pyM) * 2.0f - pyM2 - pym2;
+    const float diffy = (fabsf(pym2 - pc) + fabsf(pyM2 - pc) + fabsf(pym - pyM)) * 3.0f + (fabsf(pyM3 - pyM) + fabsf(pym3 - pym)) * 2.0f;
+    if (diffx > diffy) g = fmaxf(fminf(guessy * 0.25f, fmaxf(pym, pyM)), fminf(pym, pyM));
+    else g = fmaxf(fminf(guessx * 0.25f, fmaxf(pxm, pxM)), fminf(pxm, pxM));
+  }
+  t[0] = fmaxf(r, 0.0f), t[1] = fmaxf(g, 0.0f), t[2] = fmaxf(b, 0.0f);
+}
+
+// One pixel of the red / blue fill (ppg.cu:230-337); p = this pixel in tmp, R = floats per tmp row
+template <int kType, int R>
+__device__ __forceinline__ void ppg_fill_pixel(const float *p, bool border, float *o) {
+  float r = p[0], g = p[1], b = p[2];
+  if (!border) {
+    if (kType == 1 || kType == 2) {
+      const float *nt = p - R, *nb = p + R, *nl = p - 3, *nr = p + 3;
+      if (kType == 1) {  // the horizontal neighbours are red
+        b = (nt[2] + nb[2] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
+        r = (nl[0] + nr[0] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
+      } else {
+        r = (nt[0] + nb[0] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
+        b = (nl[2] + nr[2] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
+      }
+    } else {
+      const float *ntl = p - R - 3, *ntr = p - R + 3, *nbl = p + R - 3, *nbr = p + R + 3;
+      constexpr int k = (kType == 0) ? 2 : 0;
+      const float diff1 = fabsf(ntl[k] - nbr[k]) + fabsf(ntl[1] - g) + fabsf(nbr[1] - g);
+      const float guess1 = ntl[k] + nbr[k] + 2.0f * g - ntl[1] - nbr[1];
+      const float diff2 = fabsf(ntr[k] - nbl[k]) + fabsf(ntr[1] - g) + fabsf(nbl[1] - g);
+      const float guess2 = ntr[k] + nbl[k] + 2.0f * g - ntr[1] - nbl[1];
+      const float v = diff1 > diff2 ? guess2 * 0.5f : (diff1 < diff2 ? guess1 * 0.5f : (guess1 + guess2) * 0.25f);
+      if (kType == 0) b = v; else r = v;
+    }
+  }
+  o[0] = fmaxf(r, 0.0f), o[1] = fmaxf(g, 0.0f), o[2] = fmaxf(b, 0.0f);
+}
+
+// v1 of the two stages below ran one pixel per thread with the site colour evaluated at run time: half of the lanes idled in the
+// green stage and the two branches of the fill ran one after the other.  Here a thread owns a 2x2 quad, so all four site types
+// sit in one thread and the CFA pattern is a template argument.
+// site type of quad position (row & 1, col & 1) from the real CFA colours (the table of the bilinear kernel mirrors the
+// reference's get_pixel_type, which is not the same thing for BGGR / GBRG)
+__host__ __device__ constexpr int cfa_color(int row, int col, uint32_t filters) { return (filters >> ((((row << 1) & 14) + (col & 1)) << 1)) & 3u; }
+__host__ __device__ constexpr int ppg_type(int row, int col, uint32_t filters) {
+  const int c = cfa_color(row, col, filters);
+  return c == 0 ? 0 : (c == 2 ? 3 : (cfa_color(row, col + 1, filters) == 0 ? 1 : 2));
+}
+
+template <bool kMedian, uint32_t kFilters>
 __global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
                                                        uint32_t filters, float threshold) {
   constexpr int HC = kMedian ? 6 : 4;             // cfa halo
@@ -160,87 +249,58 @@ __global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__r
     g_in = cfa, g_stride = SC;  // HC == 4: same halo as the median patch
   }
 
-  // tmp: border_interpolate for the outer 3 px ring, PPG green elsewhere
-  for (int i = tid; i < PT * PT; i += kThreads) {
-    const int ty = i / PT, tx = i - ty * PT;
-    const int x = x0 - 1 + tx, y = y0 - 1 + ty;
-    float r = 0.0f, g = 0.0f, b = 0.0f;  // zero outside the image (ppg.cu:270)
-    if (x >= 0 && y >= 0 && x < width && y < height) {
-      const int c = fc(y, x, filters);
-      if (x < 3 || y < 3 || x >= width - 3 || y >= height - 3) {
-        // 3x3 same-colour averages of the RAW cfa clamped at 0 (ppg.cu:342-389)
-        const float *p = cfa + (ty - 1 + HC) * SC + (tx - 1 + HC);
-        float sum[3] = {0, 0, 0};
-        int cnt[3] = {0, 0, 0};
+  // tmp (34 x 34, origin (x0-1, y0-1)): border_interpolate for the outer 3 px ring, PPG green elsewhere.  Quads are aligned to even
+  // image coordinates, so the 18 x 18 quads over [x0-2, x0+34) cover it; their outermost pixels fall outside tmp and are skipped.
+  constexpr int T0 = ppg_type(0, 0, kFilters), T1 = ppg_type(0, 1, kFilters), T2 = ppg_type(1, 0, kFilters), T3 = ppg_type(1, 1, kFilters);
+  for (int i = tid; i < 18 * 18; i += kThreads) {
+    const int qy = i / 18, qx = i - qy * 18;
+    const int tx = 2 * qx - 1, ty = 2 * qy - 1;          // tmp coordinates of the quad's first pixel
+    const int x = x0 - 1 + tx, y = y0 - 1 + ty;          // image coordinates (even)
+    const bool interior = x >= 3 && y >= 3 && x + 1 < width - 3 && y + 1 < height - 3;
+    const bool c0 = tx >= 0, c1 = tx + 1 < PT, r0 = ty >= 0, r1 = ty + 1 < PT;
+    float *t = tmp + 3 * (ty * PT + tx);
+    if (interior) {
+      const float *p = g_in + (ty - 1 + 4) * g_stride + (tx - 1 + 4);
+      if (r0 && c0) ppg_tmp_pixel<T0>(p, g_stride, t);
+      if (r0 && c1) ppg_tmp_pixel<T1>(p + 1, g_stride, t + 3);
+      if (r1 && c0) ppg_tmp_pixel<T2>(p + g_stride, g_stride, t + 3 * PT);
+      if (r1 && c1) ppg_tmp_pixel<T3>(p + g_stride + 1, g_stride, t + 3 * PT + 3);
+    } else {
 #pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            const int xx = x + dx, yy = y + dy;
-            if (xx >= 0 && yy >= 0 && xx < width && yy < height) {
-              const int f = fc(yy, xx, filters);
-              const float v = fmaxf(0.0f, p[dy * SC + dx]);
-              sum[0] += f == 0 ? v : 0.0f, sum[1] += f == 1 ? v : 0.0f, sum[2] += f == 2 ? v : 0.0f;
-              cnt[0] += f == 0, cnt[1] += f == 1, cnt[2] += f == 2;
-            }
-          }
-        const float v = fmaxf(0.0f, p[0]);
-        r = cnt[0] > 0 ? sum[0] / cnt[0] : v;
-        g = cnt[1] > 0 ? sum[1] / cnt[1] : v;
-        b = cnt[2] > 0 ? sum[2] / cnt[2] : v;
-        if (c == 0) r = v; else if (c == 2) b = v; else g = v;
-      } else {
-        const float *p = g_in + (ty - 1 + 4) * g_stride + (tx - 1 + 4);
-        const float pc = p[0];
-        if (c == 0) r = pc; else if (c == 2) b = pc; else g = pc;
-        if (c != 1) {
-          const float pym = p[-g_stride], pym2 = p[-2 * g_stride], pym3 = p[-3 * g_stride];
-          const float pyM = p[g_stride], pyM2 = p[2 * g_stride], pyM3 = p[3 * g_stride];
-          const float pxm = p[-1], pxm2 = p[-2], pxm3 = p[-3], pxM = p[1], pxM2 = p[2], pxM3 = p[3];
-          const float guessx = (pxm + pc + pxM) * 2.0f - pxM2 - pxm2;
-          const float diffx = (fabsf(pxm2 - pc) + fabsf(pxM2 - pc) + fabsf(pxm - pxM)) * 3.0f + (fabsf(pxM3 - pxM) + fabsf(pxm3 - pxm)) * 2.0f;
-          const float guessy = (pym + pc + pyM) * 2.0f - pyM2 - pym2;
-          const float diffy = (fabsf(pym2 - pc) + fabsf(pyM2 - pc) + fabsf(pym - pyM)) * 3.0f + (fabsf(pyM3 - pyM) + fabsf(pym3 - pym)) * 2.0f;
-          if (diffx > diffy) g = fmaxf(fminf(guessy * 0.25f, fmaxf(pym, pyM)), fminf(pym, pyM));
-          else g = fmaxf(fminf(guessx * 0.25f, fmaxf(pxm, pxM)), fminf(pxm, pxM));
+      for (int k = 0; k < 4; k++) {
+        const int dx = k & 1, dy = k >> 1;
+        if (!((dy ? r1 : r0) && (dx ? c1 : c0))) continue;
+        const int xx = x + dx, yy = y + dy;
+        float *tp = t + 3 * (dy * PT + dx);
+        if (xx >= 3 && yy >= 3 && xx < width - 3 && yy < height - 3) {
+          const float *p = g_in + (ty + dy - 1 + 4) * g_stride + (tx + dx - 1 + 4);
+          if (k == 0) ppg_tmp_pixel<T0>(p, g_stride, tp);
+          else if (k == 1) ppg_tmp_pixel<T1>(p, g_stride, tp);
+          else if (k == 2) ppg_tmp_pixel<T2>(p, g_stride, tp);
+          else ppg_tmp_pixel<T3>(p, g_stride, tp);
+        } else {
+          ppg_tmp_border(cfa + (ty + dy - 1 + HC) * SC + (tx + dx - 1 + HC), SC, xx, yy, width, height, filters, tp);
         }
-        r = fmaxf(r, 0.0f), g = fmaxf(g, 0.0f), b = fmaxf(b, 0.0f);
       }
     }
-    tmp[3 * i] = r, tmp[3 * i + 1] = g, tmp[3 * i + 2] = b;
   }
   __syncthreads();
 
-  // red / blue fill
-  for (int i = tid; i < kTile * kTile; i += kThreads) {
-    const int ly = i / kTile, lx = i - ly * kTile;
+  // red / blue fill: one quad per thread
+  {
+    const int qx = tid & 15, qy = tid >> 4;
+    const int lx = 2 * qx, ly = 2 * qy;
     const int x = x0 + lx, y = y0 + ly;
+    constexpr int R = 3 * PT;  // one tmp row
     const float *p = tmp + 3 * ((ly + 1) * PT + lx + 1);
-    float r = p[0], g = p[1], b = p[2];
-    if (x < width && y < height && !(x == 0 || y == 0 || x == width - 1 || y == height - 1)) {
-      const int c = fc(y, x, filters);
-      constexpr int R = 3 * PT;  // one tmp row
-      if (c == 1) {
-        const float *nt = p - R, *nb = p + R, *nl = p - 3, *nr = p + 3;
-        if (fc(y, x + 1, filters) == 0) {
-          b = (nt[2] + nb[2] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
-          r = (nl[0] + nr[0] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
-        } else {
-          r = (nt[0] + nb[0] + 2.0f * g - nt[1] - nb[1]) * 0.5f;
-          b = (nl[2] + nr[2] + 2.0f * g - nl[1] - nr[1]) * 0.5f;
-        }
-      } else {
-        const float *ntl = p - R - 3, *ntr = p - R + 3, *nbl = p + R - 3, *nbr = p + R + 3;
-        const int k = (c == 0) ? 2 : 0;
-        const float diff1 = fabsf(ntl[k] - nbr[k]) + fabsf(ntl[1] - g) + fabsf(nbr[1] - g);
-        const float guess1 = ntl[k] + nbr[k] + 2.0f * g - ntl[1] - nbr[1];
-        const float diff2 = fabsf(ntr[k] - nbl[k]) + fabsf(ntr[1] - g) + fabsf(nbl[1] - g);
-        const float guess2 = ntr[k] + nbl[k] + 2.0f * g - ntr[1] - nbl[1];
-        const float v = diff1 > diff2 ? guess2 * 0.5f : (diff1 < diff2 ? guess1 * 0.5f : (guess1 + guess2) * 0.25f);
-        if (c == 0) b = v; else r = v;
-      }
-    }
-    outt[3 * i] = fmaxf(r, 0.0f), outt[3 * i + 1] = fmaxf(g, 0.0f), outt[3 * i + 2] = fmaxf(b, 0.0f);
+    float *o = outt + 3 * (ly * kTile + lx);
+    // pixels outside the image are never stored; the outermost image ring keeps its tmp value
+    const bool bx0 = x >= width || x == 0 || x == width - 1, bx1 = x + 1 >= width || x + 1 == width - 1;
+    const bool by0 = y >= height || y == 0 || y == height - 1, by1 = y + 1 >= height || y + 1 == height - 1;
+    ppg_fill_pixel<T0, R>(p, bx0 || by0, o);
+    ppg_fill_pixel<T1, R>(p + 3, bx1 || by0, o + 3);
+    ppg_fill_pixel<T2, R>(p + R, bx0 || by1, o + 3 * kTile);
+    ppg_fill_pixel<T3, R>(p + R + 3, bx1 || by1, o + 3 * kTile + 3);
   }
   __syncthreads();
   store_rgb_tile(outt, kTile * 3, rgb, x0, y0, kTile, kTile, width, height);
@@ -275,16 +335,20 @@ int launch_bilinear(const CfaSource &src, float *rgb, int width, int height, uin
 
 int launch_ppg(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, float median_threshold, cudaStream_t s) {
   dim3 block(16, 16), grid(div_up(width, kTile), div_up(height, kTile));
-  if (median_threshold > 0.0f) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(ppg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppg_smem_bytes<true>());
-      attr = true;
-    }
-    ppg_kernel<true><<<grid, block, ppg_smem_bytes<true>(), s>>>(src, rgb, width, height, filters, median_threshold / 100.0f);
-  } else {
-    ppg_kernel<false><<<grid, block, ppg_smem_bytes<false>(), s>>>(src, rgb, width, height, filters, 0.0f);
+#define TDB_PPG(CODE)                                                                                                             \
+  if (median_threshold > 0.0f) {                                                                                                  \
+    cudaFuncSetAttribute(ppg_kernel<true, CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppg_smem_bytes<true>());       \
+    ppg_kernel<true, CODE><<<grid, block, ppg_smem_bytes<true>(), s>>>(src, rgb, width, height, filters, median_threshold / 100.0f); \
+  } else {                                                                                                                        \
+    ppg_kernel<false, CODE><<<grid, block, ppg_smem_bytes<false>(), s>>>(src, rgb, width, height, filters, 0.0f);                 \
   }
+  switch (filters) {
+    case TDB_FILTERS_RGGB: TDB_PPG(TDB_FILTERS_RGGB) break;
+    case TDB_FILTERS_BGGR: TDB_PPG(TDB_FILTERS_BGGR) break;
+    case TDB_FILTERS_GRBG: TDB_PPG(TDB_FILTERS_GRBG) break;
+    default: TDB_PPG(TDB_FILTERS_GBRG) break;
+  }
+#undef TDB_PPG
   return check_launch("ppg_demosaic");
 }
 
