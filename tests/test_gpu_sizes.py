@@ -151,3 +151,12 @@ def test_estimate_white_balance(pattern):
   got = td.estimate_white_balance([torch.from_numpy(i).to(dev) for i in images], td.BayerPattern[pattern], 0.95, 8).cpu().numpy()
   np.testing.assert_allclose(got, want, rtol=2e-4)
   np.testing.assert_allclose(got, 1.0 / gains, rtol=0.02)  # the estimate is the cast (R/G, 1, B/G) of the neutral scene
+
+
+@pytest.mark.parametrize('h,w', [(516, 1100), (1030, 700), (250, 372)])
+@pytest.mark.parametrize('sigma,shadows,highlights,clarity', [(0.2, 1.0, 1.0, 0.0), (0.3, 1.4, 0.7, 0.25)])
+def test_laplacian(impl, oracle, sigma, shadows, highlights, clarity, h, w):
+  """Sizes whose replicate padding (2^(levels-1) = 256 / 512 px) is wider than a CTA's patch, so that the kernels' flat-tile paths
+  (one row / column / pixel computed and replicated) run next to the ordinary ones, at every pyramid level."""
+  lum = synth.scene_rgb(h, w, 31)[..., 1].copy()
+  check('laplacian', impl, oracle, {'sigma': sigma, 'shadows': shadows, 'highlights': highlights, 'clarity': clarity}, {'lum': lum})

@@ -84,11 +84,28 @@ struct ReduceBatch {
   __half *coarse[NP];
 };
 
+// Zones of a pyramid level in which the replicate padding is still exact: columns <= x_lo all equal column x_lo, columns >= x_hi
+// all equal column x_hi, likewise for rows.  At level 0 these are the image edges; a coarse pixel whose five fine taps lie inside a
+// zone repeats its neighbour bit for bit, so the zone of the next level is ((lo - 2) >> 1, (hi + 3) >> 1).
+struct FlatZones {
+  int x_lo, x_hi, y_lo, y_hi;
+};
+inline FlatZones coarser(const FlatZones &f) {
+  return FlatZones{f.x_lo >= 2 ? (f.x_lo - 2) >> 1 : -1, (f.x_hi + 3) >> 1, f.y_lo >= 2 ? (f.y_lo - 2) >> 1 : -1, (f.y_hi + 3) >> 1};
+}
+
 // 5x5 binomial, decimate by 2, clone a 1-px border (laplacian.cu:178-208), levels >= 2.  blockIdx.z selects the pyramid.
+// v1 staged a 35 x 35 patch with one division per element and read it back with a lane stride of two floats (two-way bank
+// conflicts on all 25 taps; ncu: 51 M conflicts, 290 instructions per coarse pixel) -- over the whole padded plane.  Here the patch
+// is split by column parity (the taps of a lane are then contiguous words), rows are staged two columns per thread, and tiles
+// inside a flat zone compute one row / column / pixel and replicate it, which removes most of the padding's share (60 % of the plane).
 constexpr int RT = 16;            // coarse tile edge
-constexpr int RP = 2 * RT + 3;    // fine patch edge
-__global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant__ ReduceBatch b, int cw, int ch, int fw, int fh) {
-  __shared__ float patch[RP][RP + 1];
+constexpr int RP = 2 * RT + 3;    // fine patch edge (35)
+constexpr int RPS = 24;           // row stride of a parity plane: 18 words used; 2 * 24 = 16 (mod 32) keeps the two half-warps apart
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant__ ReduceBatch b, int cw, int ch, int fw, int fh,
+                                                          const FlatZones fz) {
+  __shared__ float pe[RP * RPS], po[RP * RPS];  // even / odd patch columns
+  __shared__ __half res[RT][RT];
   const int k = blockIdx.z;
   const __half *__restrict__ fine = b.fine[k];
   __half *__restrict__ coarse = b.coarse[k];
@@ -96,17 +113,50 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant_
   // coarse pixel c reads fine 2*c'-2 .. 2*c'+2 with c' clamped to [1, size-2]; patch origin = 2*cx0 - 2 covers every
   // unclamped pixel of the tile, clamped border pixels are handled by reading through the same patch when possible
   const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
-  for (int i = threadIdx.x; i < RP * RP; i += kThreads) {
-    const int ly = i / RP, lx = i - ly * RP;
-    const int x = fx0 + lx, y = fy0 + ly;
-    float v = 0.0f;
-    if (x >= 0 && y >= 0 && x < fw && y < fh) {
-      v = h2f(fine[(int64_t)y * fw + x]);
+  const bool in_frame = fx0 >= 0 && fy0 >= 0 && fx0 + RP <= fw && fy0 + RP <= fh && cx0 + RT < cw && cy0 + RT < ch;
+  const bool flat_x = in_frame && (fx0 + RP - 1 <= fz.x_lo || fx0 >= fz.x_hi);
+  const bool flat_y = in_frame && (fy0 + RP - 1 <= fz.y_lo || fy0 >= fz.y_hi);
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  const int tid = threadIdx.x;
+  if (flat_x || flat_y) {
+    // constant along x and / or y: stage the distinct rows / columns only, compute the distinct outputs, replicate
+    const int nx = flat_x ? 1 : RP, ny = flat_y ? 1 : RP;
+    for (int i = tid; i < nx * ny; i += kThreads) {
+      const int ly = i / nx, lx = i - ly * nx;
+      pe[i] = h2f(fine[(int64_t)(fy0 + ly) * fw + fx0 + lx]);  // at most one row or one column: 35 values
     }
-    patch[ly][lx] = v;
+    __syncthreads();
+    const int sxm = flat_x ? 0 : 1, sym = flat_y ? 0 : 1;  // a column is stored densely (not flat in y implies flat in x here)
+    const int ncx = flat_x ? 1 : RT, ncy = flat_y ? 1 : RT;
+    for (int t = tid; t < ncx * ncy; t += kThreads) {
+      const int lx = t % ncx, ly = t / ncx;
+      const float *c = pe + (2 * ly + 2) * sym + (2 * lx + 2) * sxm;
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = -2; j <= 2; j++)
+#pragma unroll
+        for (int i = -2; i <= 2; i++) acc += c[j * sym + i * sxm] * w[i + 2] * w[j + 2];
+      res[ly][lx] = f2h(acc);
+    }
+    __syncthreads();
+    const int lx = tid & 15, ly = tid >> 4;
+    coarse[(int64_t)(cy0 + ly) * cw + cx0 + lx] = res[flat_y ? 0 : ly][flat_x ? 0 : lx];
+    return;
+  }
+  // two columns (one even, one odd) of one row per step: 35 rows x 18 column pairs
+  for (int i = tid; i < RP * 18; i += kThreads) {
+    const int ly = i / 18, kx = i - ly * 18;
+    const int x = fx0 + 2 * kx, y = fy0 + ly;
+    float ve = 0.0f, vo = 0.0f;
+    if (y >= 0 && y < fh) {
+      const __half *row = fine + (int64_t)y * fw;
+      if (x >= 0 && x < fw) ve = h2f(row[x]);
+      if (x + 1 >= 0 && x + 1 < fw && 2 * kx + 1 < RP) vo = h2f(row[x + 1]);
+    }
+    pe[ly * RPS + kx] = ve, po[ly * RPS + kx] = vo;
   }
   __syncthreads();
-  const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+  const int lx = tid & 15, ly = tid >> 4;
   const int x = cx0 + lx, y = cy0 + ly;
   if (x >= cw || y >= ch) return;
   int cx = x, cy = y;
@@ -114,15 +164,19 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant_
   if (y >= ch - 1) cy = ch - 2;
   if (cx <= 0) cx = 1;
   if (cy <= 0) cy = 1;
-  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
   float acc = 0.0f;
-  const int px = 2 * cx - fx0, py = 2 * cy - fy0;  // patch coordinates of the stencil centre
+  const int px = 2 * cx - fx0, py = 2 * cy - fy0;  // patch coordinates of the stencil centre (px is even)
   const bool inside = px >= 2 && py >= 2 && px + 2 < RP && py + 2 < RP;
   if (inside) {
+    const float *e = pe + py * RPS + (px >> 1), *o = po + py * RPS + (px >> 1);
 #pragma unroll
-    for (int j = -2; j <= 2; j++)
-#pragma unroll
-      for (int i = -2; i <= 2; i++) acc += patch[py + j][px + i] * w[i + 2] * w[j + 2];
+    for (int j = -2; j <= 2; j++) {
+      acc += e[j * RPS - 1] * w[0] * w[j + 2];
+      acc += o[j * RPS - 1] * w[1] * w[j + 2];
+      acc += e[j * RPS] * w[2] * w[j + 2];
+      acc += o[j * RPS] * w[3] * w[j + 2];
+      acc += e[j * RPS + 1] * w[4] * w[j + 2];
+    }
   } else {  // a clamped border pixel whose stencil left the staged patch (only at the far image edge)
 #pragma unroll
     for (int j = -2; j <= 2; j++)
@@ -167,7 +221,8 @@ __global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant
       const int sx = min(max(x - ms, 0), a.width - 1), sy = min(max(y - ms, 0), a.height - 1);
       v = h2f(f2h(__ldg(a.in + (int64_t)sy * a.width + sx)));
     }
-    float *cell = sm1 + ly * P1S + lx;
+    // non-flat tiles keep the even and the odd columns of a row apart (34 + 33 words): the 5 taps of a lane are then contiguous
+    float *cell = sm1 + ly * P1S + (flat_x || flat_y ? lx : (lx & 1) * 34 + (lx >> 1));
     cell[G * P1H * P1S] = v;
 #pragma unroll
     for (int k = 0; k < G; k++) cell[k * P1H * P1S] = inside ? h2f(f2h(curve(v, (k + 0.5f) / (float)G, cp))) : 0.0f;
@@ -193,7 +248,17 @@ __global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant
 #pragma unroll 1
     for (int k = 0; k < NP; k++) {
       float acc = 0.0f;
-      if (staged) {
+      if (staged && !flat_x && !flat_y) {
+        const float *e = sm1 + k * P1H * P1S + py * P1S + (px >> 1), *o = e + 34;  // px is even
+#pragma unroll
+        for (int j = -2; j <= 2; j++) {
+          acc += e[j * P1S - 1] * w[0] * w[j + 2];
+          acc += o[j * P1S - 1] * w[1] * w[j + 2];
+          acc += e[j * P1S] * w[2] * w[j + 2];
+          acc += o[j * P1S] * w[3] * w[j + 2];
+          acc += e[j * P1S + 1] * w[4] * w[j + 2];
+        }
+      } else if (staged) {
         const float *c = sm1 + k * P1H * P1S + py * sym + px * sxm;
 #pragma unroll
         for (int j = -2; j <= 2; j++)
@@ -330,11 +395,13 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
     reduce1_kernel<<<dim3(div_up(p.w[1], R1W), div_up(p.h[1], R1H)), kThreads, bytes, s>>>(r, cp);
     if (int e = check_launch("laplacian_reduce_level1")) return e;
   }
+  FlatZones fz{p.max_supp, p.max_supp + width - 1, p.max_supp, p.max_supp + height - 1};  // level 0
   for (int l = 2; l < L; l++) {
+    fz = coarser(fz);  // zones of level l - 1, the fine level of this reduction
     ReduceBatch b{};
     for (int k = 0; k < G; k++) b.fine[k] = base + p.proc[k][l - 1], b.coarse[k] = base + p.proc[k][l];
     b.fine[G] = input_level(l - 1), b.coarse[G] = input_level(l);
-    reduce_kernel<<<dim3(div_up(p.w[l], RT), div_up(p.h[l], RT), NP), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1]);
+    reduce_kernel<<<dim3(div_up(p.w[l], RT), div_up(p.h[l], RT), NP), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], fz);
     if (int e = check_launch("laplacian_reduce")) return e;
   }
   // regions of each level that can reach the cropped output: level l needs level l+1 on region/2 -+ 1
