@@ -251,16 +251,18 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
 // smoothing kernel itself was measured: the fence holds every CTA until its tile stores have landed, +12 % on that kernel):
 // ratio (postprocess.cu:362-366), bounds of the equilibrated image (x -> max(0, x * ratio) is monotone, so the extrema of the G1
 // class commute with it), image-set merge and moving average (image_processor.py:288-290)
-__global__ void __launch_bounds__(kThreads) frame_stats_kernel(const SmoothStats st, unsigned int nblk) {
-  __shared__ double dsum[2][kThreads / 32];
-  __shared__ float red[4][kThreads / 32];
+constexpr int kStatThreads = 1024;
+__global__ void __launch_bounds__(kStatThreads) frame_stats_kernel(const SmoothStats st, unsigned int nblk) {
+  __shared__ double dsum[2][kStatThreads / 32];
+  __shared__ float red[4][kStatThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double a = 0.0, b = 0.0;
   float v[4] = {FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX};
-  for (unsigned int i = tid; i < nblk; i += kThreads) {
-    const float *p = st.partials + 6 * i;
-    a += p[0], b += p[1];
-    v[0] = fminf(v[0], p[2]), v[1] = fmaxf(v[1], p[3]), v[2] = fminf(v[2], p[4]), v[3] = fmaxf(v[3], p[5]);
+  for (unsigned int i = tid; i < nblk; i += kStatThreads) {
+    const float2 *p = reinterpret_cast<const float2 *>(st.partials + 6 * i);  // 24-byte records in a 256-byte aligned array
+    const float2 s = __ldg(p), g = __ldg(p + 1), o = __ldg(p + 2);
+    a += s.x, b += s.y;
+    v[0] = fminf(v[0], g.x), v[1] = fmaxf(v[1], g.y), v[2] = fminf(v[2], o.x), v[3] = fmaxf(v[3], o.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) frame_stats_kernel(const SmoothStats
   __syncthreads();
   if (tid == 0) {
     a = b = 0.0;
-    for (int w = 0; w < kThreads / 32; w++) {
+    for (int w = 0; w < kStatThreads / 32; w++) {
       a += dsum[0][w], b += dsum[1][w];
       v[0] = fminf(v[0], red[0][w]), v[1] = fmaxf(v[1], red[1][w]), v[2] = fminf(v[2], red[2][w]), v[3] = fmaxf(v[3], red[3][w]);
     }
@@ -497,7 +499,7 @@ int tdb_postprocess_deferred(const float *in, float *out, void *scratch, int wid
   st.bounds_out = bounds_out, st.ratio_out = ratio_out;
   size_t nctas = 0;
   if (int e = run_smoothing(in, out, img_a, img_b, width, height, filters, passes, st, &nctas, s)) return e;
-  frame_stats_kernel<<<1, kThreads, 0, s>>>(st, (unsigned int)nctas);
+  frame_stats_kernel<<<1, kStatThreads, 0, s>>>(st, (unsigned int)nctas);
   return check_launch("frame_stats");
 }
 
