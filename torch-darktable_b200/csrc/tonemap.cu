@@ -128,31 +128,43 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
   const ToneConsts kc = tone_consts<kOp>(a);
 
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+  const int tw = min(kTile, width - x0), th = min(kTile, height - y0);  // valid source extent of this tile
+  if ((width & 3) == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0) {
+    // a thread owns four consecutive pixels of a tile row: three 128-bit loads (tw is a multiple of 4 here)
+    const int q = threadIdx.x & 7, ly = threadIdx.x >> 3;
+    const int x = x0 + 4 * q, y = y0 + ly;
+    if (4 * q < tw && ly < th) {
+      const float4 *src = reinterpret_cast<const float4 *>(rgb + 3 * ((int64_t)y * width + x));
+      rgb_t p[4];
+      unpack4(__ldg(src), __ldg(src + 1), __ldg(src + 2), p);
 #pragma unroll
-  for (int k = 0; k < kTile / 8; k++) {
-    const int ly = ly0 + 8 * k, x = x0 + lx, y = y0 + ly;
-    if (x < width && y < height) {
-      const float *p = rgb + 3 * ((int64_t)y * width + x);
-      tile[ly][lx] = tone_pixel<kOp, kSlice>(rgb_t{__ldg(p), __ldg(p + 1), __ldg(p + 2)}, x, y, kc, sl);
+      for (int i = 0; i < 4; i++) tile[ly][4 * q + i] = tone_pixel<kOp, kSlice>(p[i], x + i, y, kc, sl);
+    }
+  } else {
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kTile / 8; k++) {
+      const int ly = ly0 + 8 * k, x = x0 + lx, y = y0 + ly;
+      if (x < width && y < height) {
+        const float *p = rgb + 3 * ((int64_t)y * width + x);
+        tile[ly][lx] = tone_pixel<kOp, kSlice>(rgb_t{__ldg(p), __ldg(p + 1), __ldg(p + 2)}, x, y, kc, sl);
+      }
     }
   }
   __syncthreads();
 
-  // store: walk the tile in destination order so that consecutive threads write consecutive destination pixels
+  // store: walk the tile in destination order so that consecutive threads write consecutive destination bytes
   const int tf = a.transform;
   const bool swap = (tf == TDB_TF_ROTATE_90 || tf == TDB_TF_ROTATE_270 || tf == TDB_TF_TRANSPOSE);
   const int ow = swap ? height : width;
-  const int tw = min(kTile, width - x0), th = min(kTile, height - y0);  // valid source extent of this tile
   const int dw = swap ? th : tw, dh = swap ? tw : th;                   // destination extent
   int ox0, oy0, ox1, oy1;
   map_xy(tf, x0, y0, width, height, ox0, oy0);
   map_xy(tf, x0 + tw - 1, y0 + th - 1, width, height, ox1, oy1);
   const int dx0 = min(ox0, ox1), dy0 = min(oy0, oy1);
-  for (int i = threadIdx.x; i < dw * dh; i += kThreads) {
-    const int dy = i / dw, dx = i - dy * dw;
-    const int ox = dx0 + dx, oy = dy0 + dy;
-    int sx, sy;  // inverse map: which source pixel lands on (ox, oy)
+  // source pixel that lands on destination (ox, oy)
+  auto source = [&](int ox, int oy) -> uint32_t {
+    int sx, sy;
     switch (tf) {
       case TDB_TF_ROTATE_90: sx = width - 1 - oy, sy = ox; break;
       case TDB_TF_ROTATE_180: sx = width - 1 - ox, sy = height - 1 - oy; break;
@@ -163,9 +175,27 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
       case TDB_TF_TRANSVERSE: sx = width - 1 - ox, sy = height - 1 - oy; break;
       default: sx = ox, sy = oy; break;
     }
-    const uint32_t v = tile[sy - y0][sx - x0];
-    uint8_t *o = out + 3 * ((int64_t)oy * ow + ox);
-    o[0] = (uint8_t)v, o[1] = (uint8_t)(v >> 8), o[2] = (uint8_t)(v >> 16);
+    return tile[sy - y0][sx - x0];
+  };
+  if ((dw & 3) == 0 && (dx0 & 3) == 0 && (ow & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    // 32-bit stores: a destination row of the tile is dw * 3 / 4 words, each made of two neighbouring pixels
+    const int wpr = dw * 3 / 4;
+    for (int i = threadIdx.x; i < wpr * dh; i += kThreads) {
+      const int dy = i / wpr, wq = i - dy * wpr;
+      const int g = wq / 3, ph = wq - 3 * g;  // pixel group of four, word inside its twelve bytes
+      const int ox = dx0 + 4 * g + ph, oy = dy0 + dy;
+      const uint32_t va = source(ox, oy), vb = source(ox + 1, oy);
+      const uint32_t word = ph == 0 ? (va | (vb << 24)) : (ph == 1 ? ((va >> 8) | (vb << 16)) : ((va >> 16) | (vb << 8)));
+      reinterpret_cast<uint32_t *>(out + 3 * ((int64_t)oy * ow + dx0))[wq] = word;
+    }
+  } else {
+    for (int i = threadIdx.x; i < dw * dh; i += kThreads) {
+      const int dy = i / dw, dx = i - dy * dw;
+      const int ox = dx0 + dx, oy = dy0 + dy;
+      const uint32_t v = source(ox, oy);
+      uint8_t *o = out + 3 * ((int64_t)oy * ow + ox);
+      o[0] = (uint8_t)v, o[1] = (uint8_t)(v >> 8), o[2] = (uint8_t)(v >> 16);
+    }
   }
 }
 
