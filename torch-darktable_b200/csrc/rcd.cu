@@ -12,8 +12,6 @@
 // positions (or zero).  `stale_cell` reproduces exactly that for a FRESH reference workspace, so the output matches a
 // freshly constructed reference RCD object everywhere, including the band just inside the 7-px margin.  What the
 // reference leaks from the PREVIOUS frame (rows 2-3 of VH_dir) is deliberately not reproduced.
-#include <cstdlib>
-
 #include "cfa_tile.cuh"
 #include "rcd_planar.cuh"
 
@@ -55,7 +53,7 @@ __device__ float stale_cell(const CfaSource &s, bool is_p, int r, int K, int wid
   return sqr(c[0] - 3.0f * c[1] - c[2] + 6.0f * c[3] - c[4] - 3.0f * c[5] + c[6]);
 }
 
-// which 32x32 tiles a launch covers: up to four rectangles of tiles (the frame around the v2 interior), or everything
+// which 32x32 tiles a launch covers: up to four rectangles of tiles (the frame around the interior of rcd_planar.cuh), or everything
 struct TileRects {
   int n;                 // 0: plain 2-D grid over the whole image
   int tx0[4], ty0[4], ntx[4];
@@ -396,401 +394,10 @@ __global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__r
 
 
 // ======================================================================================================================
-// v2: interior tiles.  ncu of the kernel above (profiles/r01_ncu_full_v2_summary.csv): 984 thread instructions and about
-// 150 scalar shared-memory loads per output pixel, 2.6x halo recompute at 32x32, a fifth of the instructions index
-// arithmetic.  Here a CTA produces a 64x32 tile from an 88x56 patch (halo 12: every patch row and the output tile start on
-// a 16-byte boundary) and every thread owns 2 rows x 4 columns of pixels per step: the CFA / VH / v,h-diff neighbourhoods
-// come in as 128-bit shared-memory windows that the eight pixels share, both Bayer row parities sit in one thread (the
-// R/B-site steps are branch-free, the parity is a template argument), all offsets are immediates, and the result leaves
-// as three 128-bit global stores per pixel quad.  The arithmetic expressions are the ones of the kernel above, term
-// by term (the selects of RCD amplify any re-association into visible differences).
-// Only tiles whose patch lies inside the image take this path, which removes every bounds test; the frame of tiles around
-// them (and the PPG-style 7-px border) stays with the kernel above.
-namespace v2 {
-
-constexpr int TW = 64, TH = 32, HX = 12, HY = 12;
-constexpr int PW = TW + 2 * HX, PH = TH + 2 * HY;  // 88 x 56
-constexpr int HS = PW / 2;                          // half-plane row stride in cells
-constexpr int FULL = PW * PH, HALF = HS * PH;
-constexpr int O_CFA = 0, O_VH = FULL, O_LPF = 2 * FULL, O_CRB = O_LPF + HALF, O_U = O_CRB + HALF;
-constexpr int O_VD = O_U, O_HD = O_U + FULL;                                                   // phase 1
-constexpr int O_PD = O_U, O_QD = O_U + HALF, O_PQ = O_U + 2 * HALF, O_GRB = O_U + 3 * HALF;    // later phases
-constexpr int SMEM_FLOATS = O_U + 2 * FULL;
-constexpr int kThreads2 = 256;
-
-__device__ __forceinline__ float4 L4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ float2 L2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
-
-// twelve consecutive floats of a plane row: columns -4 .. 7 relative to the quad start
-struct Win {
-  float w[12];
-};
-__device__ __forceinline__ Win load_win(const float *p) {
-  const float4 l = L4(p - 4), c = L4(p), r = L4(p + 4);
-  return Win{{l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w}};
-}
-__device__ __forceinline__ float hp7(float a, float b, float c, float d, float e, float f, float g) {
-  return sqr(a - 3.0f * b - c + 6.0f * d - e - 3.0f * f + g);
-}
-
-// stage one 12-byte group (4 packed pairs = 8 pixels) of a patch row
-template <bool kIds>
-__device__ __forceinline__ void stage_group(const CfaSource &s, const uint8_t *row_bytes, int gy, int gx, float *dst) {
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(row_bytes);
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>(addr & ~uintptr_t(3));
-  const uint32_t sh = (uint32_t)(addr & 3) * 8;
-  const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = sh ? __ldg(wp + 3) : 0u;
-  const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh);
-  const uint32_t pr[4] = {x0 & 0xffffffu, (x0 >> 24) | ((x1 & 0xffffu) << 8), (x1 >> 16) | ((x2 & 0xffu) << 16), x2 >> 8};
-  float v[8];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint32_t p0, p1;
-    unpack_pair<kIds>(pr[k], p0, p1);
-    v[2 * k] = fmaxf(finish_sample(s, p0, gy, gx + 2 * k), 0.0f);
-    v[2 * k + 1] = fmaxf(finish_sample(s, p1, gy, gx + 2 * k + 1), 0.0f);
-  }
-  *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-
-// kG0: the CFA site (even row, even column) is green, i.e. the R/B sites of even rows sit on odd columns
-template <bool kG0>
-__device__ __forceinline__ void rcd2_tile(float *sm, const CfaSource &src_in, float *__restrict__ rgb, int width, int height, uint32_t filters,
-                                          int x_origin, int by_lo, int bx, int by) {
-  CfaSource src = src_in;
-  float *cfa = sm + O_CFA, *vh = sm + O_VH, *lpf = sm + O_LPF, *crb = sm + O_CRB;
-  float *vd = sm + O_VD, *hd = sm + O_HD, *pd = sm + O_PD, *qd = sm + O_QD, *pq = sm + O_PQ, *grb = sm + O_GRB;
-  resolve_gains(src, filters);
-  const int tid = threadIdx.x;
-  const int x0 = x_origin + bx * TW, y0 = (by + by_lo) * TH;
-  const int gx0 = x0 - HX, gy0 = y0 - HY;  // image coordinates of patch cell (0, 0): both even, gx0 a multiple of 4
-
-  // ---- stage the CFA patch (clamped at zero like the reference's populate step)
-  if (src.cfa) {
-    for (int i = tid; i < PH * (PW / 2); i += kThreads2) {
-      const int r = i / (PW / 2), c = (i - r * (PW / 2)) * 2;
-      const float2 v = __ldg(reinterpret_cast<const float2 *>(src.cfa + (int64_t)(gy0 + r) * width + gx0 + c));
-      *reinterpret_cast<float2 *>(cfa + r * PW + c) = make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f));
-    }
-  } else {
-    constexpr int G = PW / 8;  // 12-byte groups per patch row
-    for (int i = tid; i < PH * G; i += kThreads2) {
-      const int r = i / G, g = i - r * G;
-      const int gy = gy0 + r, gx = gx0 + 8 * g;
-      const uint8_t *b = src.packed + (((int64_t)gy * width + gx) >> 1) * 3;
-      if (src.ids) stage_group<true>(src, b, gy, gx, cfa + r * PW + 8 * g);
-      else stage_group<false>(src, b, gy, gx, cfa + r * PW + 8 * g);
-    }
-  }
-  __syncthreads();
-
-  // ---- step 1.1: squared vertical / horizontal high-pass (rcd.cu:63-75).  rows 4..51, quads 1..20
-  {
-    constexpr int NQ = 20, NB = 24 * NQ;
-    for (int i = tid; i < NB; i += kThreads2) {
-      const int rp = i / NQ, qc = 1 + i - rp * NQ;
-      const int base = (4 + 2 * rp) * PW + 4 * qc;
-      float4 c[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) c[k] = L4(cfa + base + (k - 3) * PW);
-#pragma unroll
-      for (int rho = 0; rho < 2; rho++) {
-        const float4 *m = c + rho;  // m[3] is the centre row
-        const float4 V = make_float4(hp7(m[0].x, m[1].x, m[2].x, m[3].x, m[4].x, m[5].x, m[6].x),
-                                     hp7(m[0].y, m[1].y, m[2].y, m[3].y, m[4].y, m[5].y, m[6].y),
-                                     hp7(m[0].z, m[1].z, m[2].z, m[3].z, m[4].z, m[5].z, m[6].z),
-                                     hp7(m[0].w, m[1].w, m[2].w, m[3].w, m[4].w, m[5].w, m[6].w));
-        const float4 l = L4(cfa + base + rho * PW - 4), r = L4(cfa + base + rho * PW + 4);
-        const float w[12] = {l.x, l.y, l.z, l.w, m[3].x, m[3].y, m[3].z, m[3].w, r.x, r.y, r.z, r.w};
-        const float4 Hh = make_float4(hp7(w[1], w[2], w[3], w[4], w[5], w[6], w[7]), hp7(w[2], w[3], w[4], w[5], w[6], w[7], w[8]),
-                                      hp7(w[3], w[4], w[5], w[6], w[7], w[8], w[9]), hp7(w[4], w[5], w[6], w[7], w[8], w[9], w[10]));
-        *reinterpret_cast<float4 *>(vd + base + rho * PW) = V;
-        *reinterpret_cast<float4 *>(hd + base + rho * PW) = Hh;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- step 1.2: VH_dir (rcd.cu:78-90), rows 6..49, and step 2.1: low-pass at R/B sites (rcd.cu:93-104), rows 4..51
-  {
-    constexpr int NQ = 20, NB1 = 22 * NQ, NB2 = 24 * NQ;
-    for (int i = tid; i < NB1 + NB2; i += kThreads2) {
-      if (i < NB1) {
-        const int rp = i / NQ, qc = 1 + i - rp * NQ;
-        const int base = (6 + 2 * rp) * PW + 4 * qc;
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = L4(vd + base + (k - 1) * PW);
-#pragma unroll
-        for (int rho = 0; rho < 2; rho++) {
-          const Win h = load_win(hd + base + rho * PW);
-          const float Vs[4] = {v[rho].x + v[rho + 1].x + v[rho + 2].x, v[rho].y + v[rho + 1].y + v[rho + 2].y,
-                               v[rho].z + v[rho + 1].z + v[rho + 2].z, v[rho].w + v[rho + 1].w + v[rho + 2].w};
-          float o[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const float V = fmaxf(1e-10f, Vs[j]);
-            const float Hs = fmaxf(1e-10f, h.w[3 + j] + h.w[4 + j] + h.w[5 + j]);
-            o[j] = V / (V + Hs);
-          }
-          *reinterpret_cast<float4 *>(vh + base + rho * PW) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      } else {
-        const int j2 = i - NB1;
-        const int rp = j2 / NQ, qc = 1 + j2 - rp * NQ;
-        const int v0 = 4 + 2 * rp;
-        const int base = v0 * PW + 4 * qc;
-        Win w[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) w[k] = load_win(cfa + base + (k - 1) * PW);
-#pragma unroll
-        for (int rho = 0; rho < 2; rho++) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int e = (kG0 ? 1 : 0) ^ rho;  // column parity of this row's R/B sites (compile time after unrolling)
-          float o[2];
-#pragma unroll
-          for (int t = 0; t < 2; t++) {
-            const int s = 4 + e + 2 * t;  // window index of the site
-            const float *up = w[rho].w, *ce = w[rho + 1].w, *dn = w[rho + 2].w;
-            o[t] = ce[s] + 0.5f * (up[s] + dn[s] + ce[s - 1] + ce[s + 1]) + 0.25f * (up[s - 1] + up[s + 1] + dn[s - 1] + dn[s + 1]);
-          }
-          *reinterpret_cast<float2 *>(lpf + (v0 + rho) * HS + 2 * qc) = make_float2(o[0], o[1]);
-        }
-      }
-    }
-  }
-  __syncthreads();  // vd/hd are dead from here on: the union region is reused for pd/qd/pq/grb
-
-  // ---- step 4.1: squared P/Q diagonal high-pass on odd columns (rcd.cu:149-163), rows 6..49
-  // ---- step 3.1: green at R/B sites (rcd.cu:107-146), rows 6..49
-  {
-    constexpr int NQ = 20, NB = 22 * NQ;
-    for (int i = tid; i < 2 * NB; i += kThreads2) {
-      const int j2 = i < NB ? i : i - NB;
-      const int rp = j2 / NQ, qc = 1 + j2 - rp * NQ;
-      const int v0 = 6 + 2 * rp;
-      const int base = v0 * PW + 4 * qc;
-      if (i < NB) {
-#pragma unroll
-        for (int rho = 0; rho < 2; rho++) {
-          const float *c0 = cfa + base + rho * PW;
-          float p[2], q[2];
-#pragma unroll
-          for (int t = 0; t < 2; t++) {
-            const float *c = c0 + 1 + 2 * t;
-            p[t] = sqr((c[-3 * PW - 3] - c[-PW - 1] - c[PW + 1] + c[3 * PW + 3]) - 3.0f * (c[-2 * PW - 2] + c[2 * PW + 2]) + 6.0f * c[0]);
-            q[t] = sqr((c[-3 * PW + 3] - c[-PW + 1] - c[PW - 1] + c[3 * PW - 3]) - 3.0f * (c[-2 * PW + 2] + c[2 * PW - 2]) + 6.0f * c[0]);
-          }
-          *reinterpret_cast<float2 *>(pd + (v0 + rho) * HS + 2 * qc) = make_float2(p[0], p[1]);
-          *reinterpret_cast<float2 *>(qd + (v0 + rho) * HS + 2 * qc) = make_float2(q[0], q[1]);
-        }
-      } else {
-        float4 col[10];  // rows v0-4 .. v0+5 of the quad
-#pragma unroll
-        for (int k = 0; k < 10; k++) col[k] = L4(cfa + base + (k - 4) * PW);
-#pragma unroll
-        for (int rho = 0; rho < 2; rho++) {
-          const int e = (kG0 ? 1 : 0) ^ rho;
-          const float4 l = L4(cfa + base + rho * PW - 4), r = L4(cfa + base + rho * PW + 4);
-          const float4 m = col[4 + rho];
-          const float wr[12] = {l.x, l.y, l.z, l.w, m.x, m.y, m.z, m.w, r.x, r.y, r.z, r.w};
-          const float *d0 = vh + base + rho * PW;
-          const float *lp = lpf + (v0 + rho) * HS + 2 * qc;
-          float o[2];
-#pragma unroll
-          for (int t = 0; t < 2; t++) {
-            const int s = e + 2 * t;  // site offset inside the quad
-            const float eps = 1e-5f;
-            // column of the site, rows -4 .. +4 around the centre row (col index 4 + rho)
-            float cv[9];
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-              const float4 q4 = col[rho + k];
-              cv[k] = s == 0 ? q4.x : (s == 1 ? q4.y : (s == 2 ? q4.z : q4.w));
-            }
-            const float *ch = wr + 4 + s;  // ch[-4..4] along the row
-            const float *d = d0 + s;
-            const float c0 = d[0];
-            const float nb = 0.25f * (d[-PW - 1] + d[-PW + 1] + d[PW - 1] + d[PW + 1]);
-            const float disc = (fabsf(0.5f - c0) < fabsf(0.5f - nb)) ? nb : c0;
-            const float ci = cv[4];
-            const float Ng = eps + fabsf(cv[3] - cv[5]) + fabsf(ci - cv[2]) + fabsf(cv[3] - cv[1]) + fabsf(cv[2] - cv[0]);
-            const float Sg = eps + fabsf(cv[5] - cv[3]) + fabsf(ci - cv[6]) + fabsf(cv[5] - cv[7]) + fabsf(cv[6] - cv[8]);
-            const float Wg = eps + fabsf(ch[-1] - ch[1]) + fabsf(ci - ch[-2]) + fabsf(ch[-1] - ch[-3]) + fabsf(ch[-2] - ch[-4]);
-            const float Eg = eps + fabsf(ch[1] - ch[-1]) + fabsf(ci - ch[2]) + fabsf(ch[1] - ch[3]) + fabsf(ch[2] - ch[4]);
-            const float *lq = lp + t;
-            const float li = lq[0];
-            const float Ne = cv[3] * (li + li) / (eps + li + lq[-2 * HS]);
-            const float Se = cv[5] * (li + li) / (eps + li + lq[2 * HS]);
-            const float We = ch[-1] * (li + li) / (eps + li + lq[-1]);
-            const float Ee = ch[1] * (li + li) / (eps + li + lq[1]);
-            const float Ve = (Sg * Ne + Ng * Se) / (Ng + Sg);
-            const float He = (Wg * Ee + Eg * We) / (Eg + Wg);
-            o[t] = mixf(Ve, He, disc);
-          }
-          *reinterpret_cast<float2 *>(grb + (v0 + rho) * HS + 2 * qc) = make_float2(o[0], o[1]);
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- step 4.2: PQ_dir at R/B sites (rcd.cu:166-182), rows 8..47, quads 2..19
-  {
-    constexpr int NQ = 18, NB = 20 * NQ;
-    for (int i = tid; i < NB; i += kThreads2) {
-      const int rp = i / NQ, qc = 2 + i - rp * NQ;
-      const int v0 = 8 + 2 * rp;
-#pragma unroll
-      for (int rho = 0; rho < 2; rho++) {
-        const int e = (kG0 ? 1 : 0) ^ rho;
-        float o[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const int i2 = (v0 + rho) * HS + 2 * qc + t, i3 = i2 - HS - 1 + e, i4 = i2 + HS - 1 + e;
-          const float Ps = fmaxf(1e-10f, pd[i3] + pd[i2] + pd[i4 + 1]);
-          const float Qs = fmaxf(1e-10f, qd[i3 + 1] + qd[i2] + qd[i4]);
-          o[t] = Ps / (Ps + Qs);
-        }
-        *reinterpret_cast<float2 *>(pq + (v0 + rho) * HS + 2 * qc) = make_float2(o[0], o[1]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- step 5.1: the opposite colour at R/B sites along the diagonals (rcd.cu:185-224), rows 8..47, quads 2..19
-  {
-    constexpr int NQ = 18, NB = 20 * NQ;
-    for (int i = tid; i < NB; i += kThreads2) {
-      const int rp = i / NQ, qc = 2 + i - rp * NQ;
-      const int v0 = 8 + 2 * rp;
-#pragma unroll
-      for (int rho = 0; rho < 2; rho++) {
-        const int e = (kG0 ? 1 : 0) ^ rho;
-        float o[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const float eps = 1e-5f;
-          const int s = e + 2 * t;
-          const int k = 2 * qc + t;
-          const int q1 = (v0 + rho) * HS + k, q2 = q1 - HS - 1 + e, q3 = q1 + HS - 1 + e;
-          const float c0 = pq[q1];
-          const float nb = 0.25f * (pq[q2] + pq[q2 + 1] + pq[q3] + pq[q3 + 1]);
-          const float disc = (fabsf(0.5f - c0) < fabsf(0.5f - nb)) ? nb : c0;
-          const float *c = cfa + (v0 + rho) * PW + 4 * qc + s;
-          const float g0 = grb[q1];
-          // (u - 1) >> 1 and (u + 1) >> 1 for u = 4 qc + s
-          const int kw = 2 * qc + ((s + 3) >> 1) - 2, ke = 2 * qc + ((s + 1) >> 1);
-          const float gNW = grb[q1 - HS - k + kw], gNE = grb[q1 - HS - k + ke];
-          const float gSW = grb[q1 + HS - k + kw], gSE = grb[q1 + HS - k + ke];
-          const float gNW2 = grb[q1 - 2 * HS - 1], gNE2 = grb[q1 - 2 * HS + 1];
-          const float gSW2 = grb[q1 + 2 * HS - 1], gSE2 = grb[q1 + 2 * HS + 1];
-          const float cNW = c[-PW - 1], cNE = c[-PW + 1], cSW = c[PW - 1], cSE = c[PW + 1];
-          const float NWg = eps + fabsf(cNW - cSE) + fabsf(cNW - c[-3 * PW - 3]) + fabsf(g0 - gNW2);
-          const float NEg = eps + fabsf(cNE - cSW) + fabsf(cNE - c[-3 * PW + 3]) + fabsf(g0 - gNE2);
-          const float SWg = eps + fabsf(cNE - cSW) + fabsf(cSW - c[3 * PW - 3]) + fabsf(g0 - gSW2);
-          const float SEg = eps + fabsf(cNW - cSE) + fabsf(cSE - c[3 * PW + 3]) + fabsf(g0 - gSE2);
-          const float NWe = cNW - gNW, NEe = cNE - gNE, SWe = cSW - gSW, SEe = cSE - gSE;
-          const float Pe = (NWg * SEe + SEg * NWe) / (NWg + SEg);
-          const float Qe = (NEg * SWe + SWg * NEe) / (NEg + SWg);
-          o[t] = g0 + mixf(Pe, Qe, disc);
-        }
-        *reinterpret_cast<float2 *>(crb + (v0 + rho) * HS + 2 * qc) = make_float2(o[0], o[1]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- step 5.2 at green sites + output (rcd.cu:227-282, :49-60): rows 12..43, quads 3..18, one block per thread
-  {
-    const int rp = tid >> 4, qc = 3 + (tid & 15);
-    const int v0 = HY + 2 * rp;
-    const int base = v0 * PW + 4 * qc;
-#pragma unroll
-    for (int rho = 0; rho < 2; rho++) {
-      const int e = (kG0 ? 1 : 0) ^ rho;
-      const int gy = gy0 + v0 + rho;
-      // colour of this row's R/B sites: 0 = red, 2 = blue
-      const bool row_red = fc(gy & 1, e, filters) == 0;
-      float R[4], G[4], B[4];
-      const float4 own = L4(cfa + base + rho * PW);
-      const float2 g2 = L2(grb + (v0 + rho) * HS + 2 * qc), o2 = L2(crb + (v0 + rho) * HS + 2 * qc);
-      const float ownv[4] = {own.x, own.y, own.z, own.w};
-#pragma unroll
-      for (int t = 0; t < 2; t++) {  // R/B sites
-        const int s = e + 2 * t;
-        const float g = t ? g2.y : g2.x, opp = t ? o2.y : o2.x;
-        G[s] = g;
-        R[s] = row_red ? ownv[s] : opp;
-        B[s] = row_red ? opp : ownv[s];
-      }
-#pragma unroll
-      for (int t = 0; t < 2; t++) {  // green sites
-        const int s = (1 - e) + 2 * t;
-        const float eps = 1e-5f;
-        const float *c = cfa + base + rho * PW + s;
-        const float *d = vh + base + rho * PW + s;
-        const int k = (v0 + rho) * HS + 2 * qc + ((s) >> 1);  // u >> 1
-        const int kw = (v0 + rho) * HS + 2 * qc + ((s + 3) >> 1) - 2, ke = (v0 + rho) * HS + 2 * qc + ((s + 1) >> 1);
-        const int kw3 = (v0 + rho) * HS + 2 * qc + ((s + 1) >> 1) - 2, ke3 = (v0 + rho) * HS + 2 * qc + ((s + 3) >> 1);
-        const float c0 = d[0];
-        const float nb = 0.25f * (d[-PW - 1] + d[-PW + 1] + d[PW - 1] + d[PW + 1]);
-        const float disc = (fabsf(0.5f - c0) < fabsf(0.5f - nb)) ? nb : c0;
-        const float g = c[0];
-        const float N1 = eps + fabsf(g - c[-2 * PW]), S1 = eps + fabsf(g - c[2 * PW]);
-        const float W1 = eps + fabsf(g - c[-2]), E1 = eps + fabsf(g - c[2]);
-        const float gN = grb[k - HS], gS = grb[k + HS], gW = grb[kw], gE = grb[ke];
-        float res[2];
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-          float n1, s1, w1, e1, n3, s3, w3, e3;
-          if (pass == 0) {  // the colour of this row's R/B sites: native left/right, interpolated (step 5.1) above/below
-            w1 = c[-1], e1 = c[1], w3 = c[-3], e3 = c[3];
-            n1 = crb[k - HS], s1 = crb[k + HS], n3 = crb[k - 3 * HS], s3 = crb[k + 3 * HS];
-          } else {          // the other colour: native above/below, interpolated left/right
-            n1 = c[-PW], s1 = c[PW], n3 = c[-3 * PW], s3 = c[3 * PW];
-            w1 = crb[kw], e1 = crb[ke], w3 = crb[kw3], e3 = crb[ke3];
-          }
-          const float SN = fabsf(n1 - s1), EW = fabsf(w1 - e1);
-          const float Ng = N1 + SN + fabsf(n1 - n3), Sg = S1 + SN + fabsf(s1 - s3);
-          const float Wg = W1 + EW + fabsf(w1 - w3), Eg = E1 + EW + fabsf(e1 - e3);
-          const float Ne = n1 - gN, Se = s1 - gS, We = w1 - gW, Ee = e1 - gE;
-          const float Ve = (Ng * Se + Sg * Ne) / (Ng + Sg);
-          const float He = (Eg * We + Wg * Ee) / (Eg + Wg);
-          res[pass] = g + mixf(Ve, He, disc);
-        }
-        G[s] = g;
-        R[s] = row_red ? res[0] : res[1];
-        B[s] = row_red ? res[1] : res[0];
-      }
-      float4 *o = reinterpret_cast<float4 *>(rgb + 3 * ((int64_t)gy * width + gx0 + 4 * qc));
-#define TDB_Z(v) fmaxf(v, 0.0f)
-      st_stream(o, make_float4(TDB_Z(R[0]), TDB_Z(G[0]), TDB_Z(B[0]), TDB_Z(R[1])));
-      st_stream(o + 1, make_float4(TDB_Z(G[1]), TDB_Z(B[1]), TDB_Z(R[2]), TDB_Z(G[2])));
-      st_stream(o + 2, make_float4(TDB_Z(B[2]), TDB_Z(R[3]), TDB_Z(G[3]), TDB_Z(B[3])));
-#undef TDB_Z
-    }
-  }
-}
-
-// One launch for the whole image: CTAs [0, n_interior) run the 64 x 32 interior tiles, the CTAs after them the 32 x 32 tiles of
-// the frame around the interior (kernel above).  As a launch of its own the frame is latency-bound (504 CTAs at 4K, 0.046 ms next to
-// 0.203 ms for the interior); at the end of the interior grid its CTAs fill the slots that drain.
-template <bool kG0>
-__global__ void __launch_bounds__(kThreads2, 2) rcd2_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                            uint32_t filters, int x_origin, int by_lo, int nbx, int n_interior,
-                                                            TileRects rects) {
-  extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x;
-  if (b < n_interior) rcd2_tile<kG0>(sm, src, rgb, width, height, filters, x_origin, by_lo, b % nbx, b / nbx);
-  else rcd_tile(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
-}
-
-}  // namespace v2
-
-// v3 interior tiles (rcd_planar.cuh) + the frame tiles of the kernel above in one launch, as for v2
+// Interior tiles: rcd_planar.cuh (64 x 32 tiles, 2 x 4-pixel register blocks, phase-planar shared memory).  Only tiles whose 88 x 56
+// patch lies inside the image take that path, which removes every bounds test; the frame of 32 x 32 tiles around them (and the
+// PPG-style 7-px border) stays with the kernel above and rides at the end of the same grid: as a launch of its own the frame is
+// latency-bound (504 CTAs at 4K), at the end of the interior grid its CTAs fill the slots that drain.
 template <bool kG0>
 __global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
                                                                 uint32_t filters, int x_origin, int by_lo, int nbx, int n_interior,
@@ -805,26 +412,27 @@ __global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, f
 int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, cudaStream_t s) {
   static bool attr = false;
   constexpr size_t bytes = SMEM_FLOATS * sizeof(float);
-  constexpr size_t bytes2 = v2::SMEM_FLOATS * sizeof(float);
+  constexpr size_t bytes3 = v3::SMEM_FLOATS * sizeof(float);
+  static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
   if (!attr) {
     cudaFuncSetAttribute(rcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    cudaFuncSetAttribute(v2::rcd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2);
-    cudaFuncSetAttribute(v2::rcd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2);
+    cudaFuncSetAttribute(rcd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
+    cudaFuncSetAttribute(rcd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
     attr = true;
   }
-  // v2 tiles (64 x 32) whose 88 x 56 patch lies inside the image; needs 16-byte aligned rows on both sides.  The tiling starts
-  // at x = 32 so that the frame left to the v1 kernel is a ring of single 32 x 32 tiles
+  // interior tiles (64 x 32) whose 88 x 56 patch lies inside the image; needs 16-byte aligned rows on both sides.  The tiling starts
+  // at x = 32 so that the frame left to the 32 x 32 kernel is a ring of single tiles
   const int x_origin = T;
-  const int nbx = (width - x_origin - (v2::TW + v2::HX)) / v2::TW + 1;   // x_origin + 64 bx + 76 <= width
-  const int by_lo = 1, by_hi = (height - (v2::TH + v2::HY)) / v2::TH;    // 32 by + 44 <= height
+  const int nbx = (width - x_origin - (v3::TW + v3::HX)) / v3::TW + 1;   // x_origin + 64 bx + 76 <= width
+  const int by_lo = 1, by_hi = (height - (v3::TH + v3::HY)) / v3::TH;    // 32 by + 44 <= height
   const bool aligned = (width % 4 == 0) && (reinterpret_cast<uintptr_t>(rgb) % 16 == 0) &&
                        (src.cfa ? reinterpret_cast<uintptr_t>(src.cfa) % 16 == 0
                                 : (reinterpret_cast<uintptr_t>(src.packed) % 4 == 0 && ((int64_t)width * height * 3 / 2) % 4 == 0));
   TileRects rects{};
   const int ntx = div_up(width, T), nty = div_up(height, T);
-  if (aligned && width >= x_origin + v2::TW + v2::HX && nbx >= 1 && by_hi >= by_lo) {
-    // the frame of 32 x 32 tiles around the v2 interior: top, bottom, left, right -- on the side stream, next to the interior
-    const int ix0 = x_origin / T, ix1 = (x_origin + nbx * v2::TW) / T, iy0 = by_lo * v2::TH / T, iy1 = (by_hi + 1) * v2::TH / T;
+  if (aligned && width >= x_origin + v3::TW + v3::HX && nbx >= 1 && by_hi >= by_lo) {
+    // the frame of 32 x 32 tiles around the interior: top, bottom, left, right
+    const int ix0 = x_origin / T, ix1 = (x_origin + nbx * v3::TW) / T, iy0 = by_lo * v3::TH / T, iy1 = (by_hi + 1) * v3::TH / T;
     const int rx0[4] = {0, 0, 0, ix1}, ry0[4] = {0, iy1, iy0, iy0};
     const int rnx[4] = {ntx, ntx, ix0, ntx - ix1}, rny[4] = {iy0, nty - iy1, iy1 - iy0, iy1 - iy0};
     int n = 0, total = 0;
@@ -836,30 +444,12 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     for (int k = n; k < 5; k++) rects.start[k] = total;
     for (int k = n; k < 4; k++) rects.ntx[k] = 1;
     rects.n = n;
-    static_assert(v2::SMEM_FLOATS >= SMEM_FLOATS && v2::kThreads2 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
-    static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads && v3::TW == v2::TW && v3::TH == v2::TH && v3::HX == v2::HX &&
-                  v3::HY == v2::HY, "v3 tiles the image like v2");
     const int n_interior = nbx * (by_hi - by_lo + 1);
     const int grid2 = n_interior + total;
-    static const bool use_v2 = getenv("TDB_RCD_V2") != nullptr;  // A/B switch: the row-major shared-memory layout
-    if (!use_v2) {
-      constexpr size_t bytes3 = v3::SMEM_FLOATS * sizeof(float);
-      static bool attr3 = false;
-      if (!attr3) {
-        cudaFuncSetAttribute(rcd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
-        cudaFuncSetAttribute(rcd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
-        attr3 = true;
-      }
-      if (fc(0, 0, filters) == 1)
-        rcd3_kernel<true><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
-      else
-        rcd3_kernel<false><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
-      return check_launch("rcd_demosaic");
-    }
     if (fc(0, 0, filters) == 1)
-      v2::rcd2_kernel<true><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      rcd3_kernel<true><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
     else
-      v2::rcd2_kernel<false><<<grid2, v2::kThreads2, bytes2, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      rcd3_kernel<false><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
     return check_launch("rcd_demosaic");
   }
   dim3 grid(ntx, nty);

@@ -1,17 +1,21 @@
-// RCD interior tiles, v3: the v2 kernel (rcd.cu) with every shared-memory plane stored PHASE-PLANAR.
+// RCD interior tiles: a CTA produces a 64 x 32 tile from an 88 x 56 patch (halo 12: every patch row and the output tile start on a
+// 16-byte boundary); every thread owns 2 rows x 4 columns of pixels per step, so both Bayer row parities sit in one thread (the
+// R/B-site steps are branch-free, the parity is a template argument), all offsets are immediates, and the result leaves as three
+// 128-bit global stores per pixel quad.  The arithmetic expressions are those of the 32 x 32 kernel in rcd.cu, term by term (the
+// selects of RCD amplify any re-association into visible differences).
 //
-// ncu of v2 (profiles/r01_ncu_full_v4_summary.csv; per-line wavefronts in profiles/r01_rcd2_smem_lines.txt): the kernel is
-// bound by shared-memory wavefronts (77 % of peak) and HALF of its 55 M wavefronts per 4K frame are bank-conflict replays.  A thread
-// owns a quad of 4 columns, so the lanes of a warp are 4 floats apart and every scalar neighbourhood load (the diagonals of steps
-// 4.1 / 5.1, the VH_dir crosses, the +-2 / +-3 taps of step 5.2) hits each bank four times.
+// Every shared-memory plane is stored PHASE-PLANAR.  The previous version of this kernel kept the planes row-major: ncu showed it
+// bound by shared-memory wavefronts (77 % of peak) with HALF of its 55 M wavefronts per 4K frame being bank-conflict replays -- a
+// thread owns a quad of 4 columns, so the lanes of a warp are 4 floats apart and every scalar neighbourhood load (the diagonals of
+// steps 4.1 / 5.1, the VH_dir crosses, the +-2 / +-3 taps of step 5.2) hit each bank four times.
 // Here column c of a row lives at  row * RS + (c & 3) * PQ + (c >> 2):  four planes of 22 quads per row, so that "column 4 q + m
 // of the quad q I own" is the contiguous word q + const for every m, i.e. consecutive lanes read consecutive banks whatever the
 // offset.  The half-resolution planes (cells k = c >> 1) are stored as two planes of 22 the same way.  Row strides satisfy
 // 2 * stride = 20 (mod 32): when a warp runs over the end of a row pair (20 quads) its remaining lanes continue in the banks
 // where the first ones stopped.  Every step therefore iterates 20 quads per row pair (two more than it needs in steps 4.2 / 5.1:
 // results nobody reads), and the last step, which needs 16, pairs row pairs that are 4 apart (8 * stride = 16 mod 32).
-// Vector loads become four scalar loads (same wavefronts, more instructions: the issue slots were 38 % busy).
-// The arithmetic is v2's, expression by expression.
+// Vector loads became four scalar loads (same wavefronts, more instructions: the issue slots were 38 % busy).  Result: 27 M bank
+// conflicts -> 2.8 M, 0.243 -> 0.19 ms per 4K frame, bit-identical output (profiles/r01_ncu_full_v4_summary.csv -> v5).
 #pragma once
 
 #include "cfa_tile.cuh"
@@ -248,7 +252,7 @@ __device__ __forceinline__ void rcd3_tile(float *sm, const CfaSource &src_in, fl
       const int e = (kG0 ? 1 : 0) ^ rho;
 #pragma unroll
       for (int t = 0; t < 2; t++) {
-        // v2: i2 = row * HS + 2 qc + t, i3 = i2 - HS - 1 + e, i4 = i2 + HS - 1 + e
+        // row-major cell indices of the reference: i2 = row * HS + 2 qc + t, i3 = i2 - HS - 1 + e, i4 = i2 + HS - 1 + e
         const float Ps = fmaxf(1e-10f, pdp[ho(rho - 1, t - 1 + e)] + pdp[ho(rho, t)] + pdp[ho(rho + 1, t + e)]);
         const float Qs = fmaxf(1e-10f, qdp[ho(rho - 1, t + e)] + qdp[ho(rho, t)] + qdp[ho(rho + 1, t - 1 + e)]);
         pq[(v0 - H0) * RH + qc + ho(rho, t)] = Ps / (Ps + Qs);
