@@ -144,7 +144,21 @@ __global__ void __launch_bounds__(kThreads) smooth_kernel(const float *__restric
   // ---- stage the raw patch (zero outside the image, postprocess.cu:58-59)
   float *raw = xpl;  // [PH][SPW * 3]
   const bool vec = ((width & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-  if (vec) {
+  __shared__ __align__(8) uint64_t bar;
+  if (vec && gx0 >= 0 && gy0 >= 0 && gx0 + SPW <= width && gy0 + PH <= height) {
+    // patch inside the image: every patch row is 768 contiguous, 16-byte aligned bytes of the frame -> one bulk asynchronous copy
+    // per row (cp.async.bulk, the 1-D form of the TMA engine) issued by the lanes of warp 0, completion through an mbarrier; no
+    // thread spends issue slots or registers on moving the 29 KB
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+      if (tid == 0) mbar_arrive_expect_tx(&bar, (uint32_t)(PH * SPW * 3 * sizeof(float)));
+      __syncwarp();
+      for (int ly = tid; ly < PH; ly += 32)
+        bulk_copy_g2s(raw + ly * SPW * 3, in + 3 * ((int64_t)(gy0 + ly) * width + gx0), (uint32_t)(SPW * 3 * sizeof(float)), &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else if (vec) {
     constexpr int QR = SPW * 3 / 4;  // float4 per patch row
     for (int i = tid; i < PH * QR; i += kThreads) {
       const int ly = i / QR, q = i - ly * QR;
