@@ -97,8 +97,10 @@ __device__ __forceinline__ void stage_patch(float *smem, int stride, int px0, in
   }
 }
 
-// Write a (tw x th) RGB tile held in smem (row stride `sstride` floats, 3 floats per pixel) to the image.
-// Uses 128-bit stores when the destination rows are 16-byte aligned (width % 4 == 0 and x0 % 4 == 0).
+// Write a (tw x th) RGB tile held in smem (row stride `sstride` floats, 3 floats per pixel) to the image.  All threads of the CTA
+// call it, after the barrier that completes the tile.  When the destination rows are 16-byte aligned (width % 4 == 0 and
+// x0 % 4 == 0) every row leaves as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the 1-D form of the TMA engine),
+// issued by the lanes of warp 0; otherwise with 128-bit or scalar stores.
 __device__ __forceinline__ void store_rgb_tile(const float *smem, int sstride, float *__restrict__ rgb, int x0, int y0, int tw,
                                                int th, int width, int height) {
   const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -106,7 +108,15 @@ __device__ __forceinline__ void store_rgb_tile(const float *smem, int sstride, f
   if (vw <= 0 || vh <= 0) return;
   const bool vec = ((width & 3) == 0) && ((x0 & 3) == 0) && ((vw & 3) == 0) && ((sstride & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(rgb) & 15) == 0);
-  if (vec) {
+  if (vec && (smem_addr(smem) & 15) == 0) {
+    bulk_store_fence();   // this thread's writes of the tile -> visible to the asynchronous proxy
+    __syncthreads();
+    if (tid < 32) {
+      for (int ly = tid; ly < vh; ly += 32)
+        bulk_copy_s2g(rgb + 3 * ((int64_t)(y0 + ly) * width + x0), smem + ly * sstride, (uint32_t)(vw * 3 * sizeof(float)));
+      bulk_store_commit_and_drain();
+    }
+  } else if (vec) {
     const int qrow = vw * 3 / 4;  // float4 per row
     for (int i = tid; i < qrow * vh; i += nthreads) {
       const int ly = i / qrow, q = i - ly * qrow;

@@ -110,6 +110,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gm
                "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+// shared -> global: the writers of the shared-memory tile call bulk_store_fence() before the barrier that precedes the copy
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit_and_drain() {  // until the shared-memory source may be overwritten / released
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
   asm volatile(
       "{\n"
