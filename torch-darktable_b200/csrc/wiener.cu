@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
   unsigned int *counter = a.counters;
   __shared__ unsigned int s_base;
   for (;;) {
-    // dynamic scheduling: a CTA claims kWarps consecutive jobs (neighbours in x: shared lines in L1) at a time
+    // dynamic scheduling: a CTA claims kWarps consecutive jobs (neighbours in x: shared lines in L1) at a time.
+    // (Claiming one step ahead and prefetching the next pair's rows into L1 -- prefetch.global.L1, SASS CCTL.E.PF1 -- was
+    // measured: 0.285 -> 0.300 ms; without the prefetch the single-barrier variant is a wash.)
     __syncthreads();
     if (threadIdx.x == 0) s_base = atomicAdd(counter, (unsigned int)kWarps);
     __syncthreads();
