@@ -44,7 +44,7 @@ ALG_BYTES = {
   'bilateral_zero_grid': GRID_BPP, 'bilateral_splat': 12.0 + GRID_BPP, 'bilateral_blur': 2 * GRID_BPP,
   'bilateral_slice': 24.0, 'metrics_init': 0.0, 'compute_image_metrics': 12.0 / 64, 'metrics_finalize': 0.0, 'tonemap': 15.0,
   # fused frame pipeline
-  'frame_prepare': 12.0 + 12.0 + 4.0 + 4.0, 'wiener_normalize_lum': 28.0 + 4.0, 'bilateral_grid_build': 4.0 + GRID_BPP,
+  'frame_prepare': 12.0 + 8.0 + 4.0 + 4.0, 'wiener_normalize_lum': 24.0 + 4.0, 'bilateral_grid_build': 4.0 + GRID_BPP,
   'metrics_sliced': 12.0 / 64, 'frame_stats': 0.0,
   'bilateral_slice_tonemap': 15.0,
 }

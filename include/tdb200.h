@@ -219,12 +219,15 @@ size_t tdb_frame_state_bytes(void);
 int tdb_postprocess_deferred(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
                              int bounds_stride, void *frame_state, int first_in_set, int last_in_set, const float *prev_bounds,
                              float moving_average, float *bounds_out, float *ratio_out, tdb_stream_t stream);
-/* out = normalize(green_eq_global(rgb, ratio), bounds); ratio == NULL skips the equilibration.  wiener_scratch != NULL:
- * also writes log(max(eps, L(out))) into the scratch's luminance plane and clears its accumulator and job counters.      */
+/* c = normalize(green_eq_global(rgb, ratio), bounds); ratio == NULL skips the equilibration.
+ * wiener_scratch == NULL: out (H,W,3) = c.
+ * wiener_scratch != NULL: out (H,W,2) = the Lab (a, b) pair of c (rgb_to_lab), log(max(eps, L(c))) goes into the scratch's
+ * luminance plane and its accumulator and job counters are cleared: what tdb_wiener_log_luminance_fused(prepared = 2) needs. */
 int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch, int width, int height, uint32_t filters,
                       const float *ratio, const float *bounds, float eps, tdb_stream_t stream);
-/* tdb_wiener_log_luminance with two options: prepared != 0 = the scratch was filled by tdb_frame_prepare;
- * bilateral_scratch != NULL = also build the blurred bilateral grid of the OUTPUT image there (zero + splat + blur).     */
+/* tdb_wiener_log_luminance with two options.  prepared: 0 = plain; 1 = the scratch holds log-luminance and a cleared
+ * accumulator, rgb is the colour image; 2 = as 1 and `rgb` is the (H,W,2) Lab (a, b) plane written by tdb_frame_prepare.
+ * bilateral_scratch != NULL = also build the blurred bilateral grid of the OUTPUT image there (luminance plane + grid).   */
 int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap,
                                    float noise, float eps, int prepared, void *bilateral_scratch, float sigma_s, float sigma_r,
                                    tdb_stream_t stream);

@@ -1,9 +1,12 @@
 // Pointwise glue of the fused frame pipeline (include/tdb200.h, "Fused frame pipeline").
 //
 //   frame_prepare  : global green equilibration (the ratio comes from the smoothing kernel's statistics) + normalisation with the
-//                    image-set bounds + log-luminance for the Wiener tiles + clearing of the Wiener accumulator, in one pass:
-//                    12 B read, 12 + 4 + 4 B written per pixel.  Replaces green_eq_kernel -> normalize_kernel -> loglum_kernel
-//                    -> memset (24 + 24 + 16 + 4 B/px, four launches); the arithmetic per pixel is the same, term by term.
+//                    image-set bounds + log-luminance for the Wiener tiles + clearing of the Wiener accumulator, in one pass.
+//                    Replaces green_eq_kernel -> normalize_kernel -> loglum_kernel -> memset (24 + 24 + 16 + 4 B/px, four launches);
+//                    the arithmetic per pixel is the same, term by term.  When the Wiener stage follows, the normalised colour
+//                    leaves as its Lab (a, b) pair instead of RGB (12 B read, 8 + 4 + 4 B written per pixel): the write-back of the
+//                    denoised luminance (modify_log_luminance) needs exactly rgb_to_lab(colour).a/b, and computing it here shares
+//                    the linearisation with the log-luminance, which saves the write-back pass six of its fifteen pow().
 //   metrics_sliced : compute_image_metrics (color_adaption.cu:121-166) of the image the bilateral slice WOULD produce, evaluated
 //                    only at the sampled pixels (every stride-th), so that the slice itself can be fused into the tone-map kernel
 //                    and the locally contrasted image never exists in HBM.  The last CTA merges the sums into the image set and
@@ -26,7 +29,7 @@ inline int flat_grid(int64_t items) {
 struct PrepareArgs {
   const float *in;
   float *out;
-  float *loglum;        // or null
+  float *loglum;        // or null; with it, `out` receives Lab (a, b) pairs instead of RGB
   float *zero;          // plane to clear (the Wiener accumulator), or null
   unsigned int *counters;  // two job counters of the Wiener tile kernels to clear, or null
   const float *ratio;   // device float[1], or null = no equilibration
@@ -43,7 +46,17 @@ __device__ __forceinline__ rgb_t prepare_pixel(rgb_t c, bool g1, bool eq, float 
   }
   return rgb_t{(c.x - b0) / range, (c.y - b0) / range, (c.z - b0) / range};  // normalize_kernel
 }
-__device__ __forceinline__ float log_luminance(rgb_t c, float eps) { return logf(fmaxf(eps, pub::luminance(c))); }
+// (a, b) of rgb_to_lab(c) and log(max(eps, compute_luminance(c))).  compute_luminance clips the colour first; inside [0,1]^3 the clip
+// is the identity and its L is the L of the same Lab conversion (same expressions as pub::rgb_to_lab / pub::luminance)
+__device__ __forceinline__ float2 lab_ab_and_loglum(rgb_t c, float eps, float &loglum) {
+  const bool inside = c.x >= 0.0f && c.x <= 1.0f && c.y >= 0.0f && c.y <= 1.0f && c.z >= 0.0f && c.z <= 1.0f;
+  const rgb_t v = pub::rgb_to_xyz(c);
+  const float fx = pub::lab_f(v.x / 0.95047f), fy = pub::lab_f(v.y / 1.0f), fz = pub::lab_f(v.z / 1.08883f);
+  float L = fmaxf(0.0f, (116.0f / 100.0f) * fy - (16.0f / 100.0f));
+  if (!inside) L = pub::luminance(c);
+  loglum = logf(fmaxf(eps, L));
+  return make_float2((500.0f / 128.0f) * (fx - fy), (200.0f / 128.0f) * (fy - fz));
+}
 
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) {
@@ -66,21 +79,33 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) 
       unpack4(ld_stream(src), ld_stream(src + 1), ld_stream(src + 2), p);
 #pragma unroll
       for (int k = 0; k < 4; k++) p[k] = prepare_pixel(p[k], even_row && ((k & 1) == g1_col), eq, ratio, b0, range);
-      float4 o0, o1, o2;
-      pack4(p, o0, o1, o2);
-      float4 *dst = reinterpret_cast<float4 *>(a.out) + 3 * g;
-      dst[0] = o0, dst[1] = o1, dst[2] = o2;
-      if (a.loglum)
-        reinterpret_cast<float4 *>(a.loglum)[g] =
-            make_float4(log_luminance(p[0], a.eps), log_luminance(p[1], a.eps), log_luminance(p[2], a.eps), log_luminance(p[3], a.eps));
+      if (a.loglum) {
+        float ll[4];
+        float2 ab[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ab[k] = lab_ab_and_loglum(p[k], a.eps, ll[k]);
+        float4 *dst = reinterpret_cast<float4 *>(a.out) + 2 * g;
+        dst[0] = make_float4(ab[0].x, ab[0].y, ab[1].x, ab[1].y), dst[1] = make_float4(ab[2].x, ab[2].y, ab[3].x, ab[3].y);
+        reinterpret_cast<float4 *>(a.loglum)[g] = make_float4(ll[0], ll[1], ll[2], ll[3]);
+      } else {
+        float4 o0, o1, o2;
+        pack4(p, o0, o1, o2);
+        float4 *dst = reinterpret_cast<float4 *>(a.out) + 3 * g;
+        dst[0] = o0, dst[1] = o1, dst[2] = o2;
+      }
       if (a.zero) reinterpret_cast<float4 *>(a.zero)[g] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
   } else {
     for (int64_t i = t0; i < n; i += stride) {
       const int y = (int)(i / a.width), x = (int)(i - (int64_t)y * a.width);
       const rgb_t p = prepare_pixel(rgb_t{a.in[3 * i], a.in[3 * i + 1], a.in[3 * i + 2]}, !(y & 1) && ((x & 1) == g1_col), eq, ratio, b0, range);
-      a.out[3 * i] = p.x, a.out[3 * i + 1] = p.y, a.out[3 * i + 2] = p.z;
-      if (a.loglum) a.loglum[i] = log_luminance(p, a.eps);
+      if (a.loglum) {
+        float ll;
+        const float2 ab = lab_ab_and_loglum(p, a.eps, ll);
+        a.out[2 * i] = ab.x, a.out[2 * i + 1] = ab.y, a.loglum[i] = ll;
+      } else {
+        a.out[3 * i] = p.x, a.out[3 * i + 1] = p.y, a.out[3 * i + 2] = p.z;
+      }
       if (a.zero) a.zero[i] = 0.0f;
     }
   }

@@ -436,7 +436,8 @@ struct NormArgs {
   float *lum_out;
 };
 
-template <bool kLogLum, bool kSplat>
+// kAb: `rgb` holds the Lab (a, b) pairs of the colour (frame_prepare) instead of the colour itself
+template <bool kLogLum, bool kSplat, bool kAb = false>
 __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a) {
   __shared__ float m1[32];  // 1-D mask factor per phase: sum_j win[r + j*stride]^2
   if (threadIdx.x < a.stride) {
@@ -451,8 +452,14 @@ __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a)
     const float mask = m1[x % a.stride] * m1[y % a.stride];
     if (kLogLum) {
       const float l = __ldg(a.acc + i) / (mask + kEps);
-      const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
-      const rgb_t r = pub::with_luminance(c, expf(l));
+      rgb_t r;
+      if (kAb) {  // pub::with_luminance with rgb_to_lab(c).a/b already at hand
+        const float2 ab = __ldg(reinterpret_cast<const float2 *>(a.rgb) + i);
+        r = clip01(pub::lab_to_rgb(rgb_t{fmaxf(0.0f, fminf(1.0f, expf(l))), ab.x, ab.y}));
+      } else {
+        const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
+        r = pub::with_luminance(c, expf(l));
+      }
       a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
       if (kSplat) a.lum_out[i] = pub::luminance(r);
     } else {
@@ -594,7 +601,7 @@ int tdb_wiener(const float *in, float *out, void *scratch, int width, int height
 }
 
 static int run_log_luminance(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap, float noise,
-                             float eps, bool prepared, void *bilateral_scratch, float sigma_s, float sigma_r, cudaStream_t s) {
+                             float eps, int prepared, void *bilateral_scratch, float sigma_s, float sigma_r, cudaStream_t s) {
   const WienerScratch ws = wiener_scratch(scratch, width, height, 1);
   const int64_t px = (int64_t)width * height;
   const int grid = (int)((px + 255) / 256 < kNumSMs * 16 ? (px + 255) / 256 : kNumSMs * 16);
@@ -608,15 +615,18 @@ static int run_log_luminance(const float *rgb, float *out, void *scratch, int wi
     g = bil::grid_dims(width, height, sigma_s, sigma_r);
     n.lum_out = bilateral_lum_plane(bilateral_scratch, g);
   }
-  if (int e = run_tiles(ws.lum, ws.acc, width, height, 1, tile, overlap, nullptr, noise, s, prepared)) return e;
+  if (int e = run_tiles(ws.lum, ws.acc, width, height, 1, tile, overlap, nullptr, noise, s, prepared != 0)) return e;
   n.acc = ws.acc, n.rgb = rgb, n.out = out, n.width = width, n.height = height, n.channels = 1, n.K = tile, n.stride = tile / overlap;
   make_window(tile, n.win);
+  const bool ab = prepared == 2;
   if (bilateral_scratch) {
-    wiener_normalize_kernel<true, true><<<grid, 256, 0, s>>>(n);
+    if (ab) wiener_normalize_kernel<true, true, true><<<grid, 256, 0, s>>>(n);
+    else wiener_normalize_kernel<true, true><<<grid, 256, 0, s>>>(n);
     if (int e = check_launch("wiener_normalize_lum")) return e;
     return bilateral_build_grid(bilateral_scratch, n.lum_out, width, height, g, sigma_s, sigma_r, s);
   }
-  wiener_normalize_kernel<true, false><<<grid, 256, 0, s>>>(n);
+  if (ab) wiener_normalize_kernel<true, false, true><<<grid, 256, 0, s>>>(n);
+  else wiener_normalize_kernel<true, false><<<grid, 256, 0, s>>>(n);
   return check_launch("wiener_normalize");
 }
 
@@ -625,7 +635,7 @@ int tdb_wiener_log_luminance(const float *rgb, float *out, void *scratch, int wi
   TDB_REQUIRE(rgb && out && scratch, "Wiener: null pointer");
   TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
   if (int e = check_args(width, height, 1, tile, overlap)) return e;
-  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, false, nullptr, 0.0f, 0.0f, as_stream(stream));
+  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, 0, nullptr, 0.0f, 0.0f, as_stream(stream));
 }
 
 int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap, float noise,
@@ -634,7 +644,8 @@ int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, 
   TDB_REQUIRE(eps > 0.0f, "Epsilon must be positive");
   TDB_REQUIRE(!bilateral_scratch || (sigma_r > 0.0f && sigma_s > 0.0f), "Bilateral: invalid sigmas");
   if (int e = check_args(width, height, 1, tile, overlap)) return e;
-  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, prepared != 0, bilateral_scratch, sigma_s, sigma_r,
+  TDB_REQUIRE(prepared >= 0 && prepared <= 2, "Wiener: prepared must be 0, 1 or 2");
+  return run_log_luminance(rgb, out, scratch, width, height, tile, overlap, noise, eps, prepared, bilateral_scratch, sigma_s, sigma_r,
                            as_stream(stream));
 }
 

@@ -731,9 +731,10 @@ class FramePipeline:
     return out, ratio
 
   def prepare(self, rgb: torch.Tensor, ratio: torch.Tensor | None, bounds: torch.Tensor, wiener: 'Wiener | None', eps: float = 1e-4):
-    """green_eq_global (ratio) + normalize (bounds) [+ log-luminance and accumulator clear into the Wiener scratch]."""
+    """green_eq_global (ratio) + normalize (bounds).  With `wiener` the result is the (H, W, 2) Lab (a, b) plane of the normalised
+    colour, and its log-luminance and a cleared accumulator sit in the Wiener scratch: the input of `denoise(..., prepared=True)`."""
     _rgb_image(rgb)
-    out = torch.empty_like(rgb)
+    out = torch.empty_like(rgb) if wiener is None else torch.empty((self._height, self._width, 2), dtype=torch.float32, device=rgb.device)
     scratch = wiener._ensure_scratch(lib.tdb_wiener_scratch_bytes(self._width, self._height, 1, wiener._tile)) if wiener is not None else None
     with torch.cuda.device(self._device):
       check(lib.tdb_frame_prepare(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, self._filters, _ptr(ratio), _ptr(bounds),
@@ -741,15 +742,20 @@ class FramePipeline:
     return out
 
   def denoise(self, wiener: 'Wiener', rgb: torch.Tensor, noise: float, prepared: bool, bilateral: 'Bilateral | None', eps: float = 1e-4):
-    """Wiener.process_log_luminance; with `bilateral` the blurred grid of the result is built in its scratch on the way."""
-    _rgb_image(rgb)
-    out = torch.empty_like(rgb)
+    """Wiener.process_log_luminance; with `bilateral` the blurred grid of the result is built in its scratch on the way.
+    prepared: `rgb` is what `prepare(..., wiener)` returned (the Lab (a, b) plane)."""
+    if prepared:
+      _require(rgb.is_cuda and rgb.dtype == torch.float32 and rgb.is_contiguous() and rgb.shape == (self._height, self._width, 2),
+               'prepared input must be the (H, W, 2) plane returned by prepare()')
+    else:
+      _rgb_image(rgb)
+    out = torch.empty((self._height, self._width, 3), dtype=torch.float32, device=rgb.device)
     scratch = wiener._ensure_scratch(lib.tdb_wiener_scratch_bytes(self._width, self._height, 1, wiener._tile))
     grid = bilateral._grid_scratch() if bilateral is not None else None
     ss, sr = (bilateral._sigma_s, bilateral._sigma_r) if bilateral is not None else (0.0, 0.0)
     with torch.cuda.device(self._device):
       check(lib.tdb_wiener_log_luminance_fused(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, wiener._tile,
-                                               wiener._overlap, float(noise), float(eps), int(prepared), _ptr(grid), ss, sr, self._s()))
+                                               wiener._overlap, float(noise), float(eps), 2 if prepared else 0, _ptr(grid), ss, sr, self._s()))
     return out
 
   def bilateral_grid(self, bilateral: 'Bilateral', rgb: torch.Tensor):
