@@ -227,17 +227,19 @@ int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch, int wi
                       const float *ratio, const float *bounds, float eps, tdb_stream_t stream);
 /* tdb_wiener_log_luminance with two options.  prepared: 0 = plain; 1 = the scratch holds log-luminance and a cleared
  * accumulator, rgb is the colour image; 2 = as 1 and `rgb` is the (H,W,2) Lab (a, b) plane written by tdb_frame_prepare.
- * bilateral_scratch != NULL = also build the blurred bilateral grid of the OUTPUT image there (luminance plane + grid).   */
+ * bilateral_scratch != NULL = also build the blurred bilateral grid of the OUTPUT image there (luminance plane + grid);
+ * `out` then receives rgb_to_lab(result) instead of the result: pass it on with lab_input = 1 below.                     */
 int tdb_wiener_log_luminance_fused(const float *rgb, float *out, void *scratch, int width, int height, int tile, int overlap,
                                    float noise, float eps, int prepared, void *bilateral_scratch, float sigma_s, float sigma_r,
                                    tdb_stream_t stream);
 /* compute_image_metrics(stride, min_gray) of Bilateral.process_rgb(rgb, detail) given the blurred grid in
- * bilateral_scratch (NULL: of rgb itself), accumulated over the image set.  metrics_out: device float[5].                */
-int tdb_metrics_sliced(const float *rgb, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r,
+ * bilateral_scratch (NULL: of rgb itself), accumulated over the image set.  metrics_out: device float[5].
+ * lab_input != 0: `rgb` holds rgb_to_lab of the image (the output of tdb_wiener_log_luminance_fused with a grid).        */
+int tdb_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r,
                        float detail, int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set,
                        const float *prev_metrics, float moving_average, float *metrics_out, tdb_stream_t stream);
 /* tdb_tonemap of Bilateral.process_rgb(rgb, detail) given the blurred grid in bilateral_scratch.                         */
-int tdb_bilateral_slice_tonemap(const float *rgb, const void *bilateral_scratch, uint8_t *out, int width, int height,
+int tdb_bilateral_slice_tonemap(const float *rgb, int lab_input, const void *bilateral_scratch, uint8_t *out, int width, int height,
                                 float sigma_s, float sigma_r, float detail, int op, const float *metrics, float gamma,
                                 float intensity, float light_adapt, float vibrance, const float *matrix, int transform,
                                 tdb_stream_t stream);

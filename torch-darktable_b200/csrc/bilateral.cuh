@@ -74,6 +74,14 @@ __device__ __forceinline__ rgb_t slice_rgb(const float *__restrict__ grid, int x
   return clip01(pub::lab_to_rgb(lab));
 }
 
+// The same step for a colour that is already in Lab (what the fused Wiener write-back leaves behind for a clipped colour r:
+// rgb_to_lab(r), whose L is compute_luminance(r) because r is inside [0,1]^3): no forward conversion at all.
+__device__ __forceinline__ rgb_t slice_lab(const float *__restrict__ grid, int x, int y, rgb_t lab, GridDims g, float sigma_s, float sigma_r,
+                                           float detail) {
+  const float Lout = slice_luminance(grid, x, y, fmaxf(0.0f, lab.x), g, sigma_s, sigma_r, detail);
+  return clip01(pub::lab_to_rgb(rgb_t{fmaxf(0.0f, fminf(1.0f, Lout)), lab.y, lab.z}));
+}
+
 // splat of one pixel into the grid with native red.global.add.f32 (reference bilateral.cu:89-129).  A zero weight leaves the cell
 // unchanged, so its atomic is skipped: for integer sigma_s the fractions are multiples of 1/sigma_s and on average only 4.5 of the 8
 // corners carry weight at sigma_s = 2

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) 
 struct MetricsArgs {
   const float *rgb;
   const float *grid;  // blurred bilateral grid, or null = measure rgb as it is
+  int lab_input;      // the image holds Lab pixels (fused Wiener write-back) instead of RGB
   bil::GridDims g;
   float sigma_s, sigma_r, detail;
   int width, height, stride, sw;
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsA
     const int x = sx * a.stride, y = sy * a.stride;
     const float *p = a.rgb + 3 * ((int64_t)y * a.width + x);
     rgb_t c{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-    if (a.grid) c = bil::slice_rgb(a.grid, x, y, c, a.g, a.sigma_s, a.sigma_r, a.detail);
+    if (a.grid) c = a.lab_input ? bil::slice_lab(a.grid, x, y, c, a.g, a.sigma_s, a.sigma_r, a.detail)
+                                : bil::slice_rgb(a.grid, x, y, c, a.g, a.sigma_s, a.sigma_r, a.detail);
     const float r = (c.x - b0) / range, g = (c.y - b0) / range, b = (c.z - b0) / range;
     const float mask = (r >= 0.99f || g >= 0.99f || b >= 0.99f) ? 0.0f : 1.0f;
     const float gray = r * 0.299f + g * 0.587f + b * 0.114f;
@@ -208,13 +210,14 @@ int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch_buf, in
   return check_launch("frame_prepare");
 }
 
-int tdb_metrics_sliced(const float *rgb, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r, float detail,
+int tdb_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r, float detail,
                        int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set, const float *prev_metrics,
                        float moving_average, float *metrics_out, tdb_stream_t stream) {
   TDB_REQUIRE(rgb && frame_state && metrics_out, "metrics_sliced: null pointer");
   TDB_REQUIRE(width > 0 && height > 0 && stride > 0, "metrics_sliced: bad arguments");
   MetricsArgs a{};
-  a.rgb = rgb;
+  a.rgb = rgb, a.lab_input = lab_input;
+  TDB_REQUIRE(!lab_input || bilateral_scratch, "metrics_sliced: a Lab image needs the bilateral grid");
   if (bilateral_scratch) {
     TDB_REQUIRE(sigma_r > 0.0f && sigma_s > 0.0f, "metrics_sliced: invalid sigmas");
     a.g = bil::grid_dims(width, height, sigma_s, sigma_r);

@@ -22,7 +22,7 @@ struct TonemapArgs {
   int op, transform;
 };
 
-// kSlice: the pixel is produced by the bilateral slice (Bilateral.process_rgb's last step) instead of being read as is, so the
+// kSlice (1: the image is RGB, 2: the image is Lab): the pixel is produced by the bilateral slice (Bilateral.process_rgb's last step) instead of being read as is, so the
 // locally contrasted image is never written to HBM: 12 B read + 3 B written per pixel for slice + tone map together.
 struct SliceArgs {
   const float *grid;  // blurred bilateral grid
@@ -71,9 +71,10 @@ __device__ __forceinline__ ToneConsts tone_consts(const TonemapArgs &a) {
   return k;
 }
 // one pixel: [slice] -> [3x3] -> tone curve -> gamma -> vibrance -> 0x00BBGGRR
-template <int kOp, bool kSlice>
+template <int kOp, int kSlice>
 __device__ __forceinline__ uint32_t tone_pixel(rgb_t c, int x, int y, const ToneConsts &k, const SliceArgs &sl) {
-  if (kSlice) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
+  if (kSlice == 1) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
+  if (kSlice == 2) c = bil::slice_lab(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);  // the input pixel is Lab
   if (k.has_matrix) c = mat3(k.m, c);
   rgb_t t;
   if (kOp == TDB_TM_ACES) {
@@ -94,7 +95,7 @@ __device__ __forceinline__ uint32_t tone_pixel(rgb_t c, int x, int y, const Tone
 
 // Transforms that keep rows as rows (none, flips, rotate_180): a thread owns four consecutive pixels of a row -- three 128-bit
 // loads, three 32-bit stores of the twelve result bytes -- and no shared-memory tile is needed.  width % 4 == 0.
-template <int kOp, bool kSlice>
+template <int kOp, int kSlice>
 __global__ void __launch_bounds__(kThreads) tonemap_rows_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, int width,
                                                                 int height, TonemapArgs a, SliceArgs sl) {
   const ToneConsts k = tone_consts<kOp>(a);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) tonemap_rows_kernel(const float *__r
   }
 }
 
-template <int kOp, bool kSlice>
+template <int kOp, int kSlice>
 __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, int width,
                                                            int height, TonemapArgs a, SliceArgs sl) {
   __shared__ uint32_t tile[kTile][kTile + 1];  // 0x00BBGGRR per pixel, indexed [y][x] in SOURCE tile coordinates
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
 
 using namespace tdb;
 
-template <bool kSlice>
+template <int kSlice>
 static int launch_tonemap(const float *rgb, uint8_t *out, int width, int height, const TonemapArgs &a, const SliceArgs &sl, cudaStream_t s,
                           const char *name) {
   const bool rows = a.transform == TDB_TF_NONE || a.transform == TDB_TF_FLIP_HORIZ || a.transform == TDB_TF_FLIP_VERT ||
@@ -241,11 +242,11 @@ int tdb_tonemap(const float *rgb, uint8_t *out, int width, int height, int op, c
   TDB_REQUIRE(op == TDB_TM_ACES || metrics, "tonemap: metrics required");
   TDB_REQUIRE(transform >= TDB_TF_NONE && transform <= TDB_TF_TRANSVERSE, "tonemap: bad transform %d", transform);
   TonemapArgs a{gamma, intensity, light_adapt, vibrance, metrics, matrix, op, transform};
-  return launch_tonemap<false>(rgb, out, width, height, a, SliceArgs{}, as_stream(stream), "tonemap");
+  return launch_tonemap<0>(rgb, out, width, height, a, SliceArgs{}, as_stream(stream), "tonemap");
 }
 
-int tdb_bilateral_slice_tonemap(const float *rgb, const void *bilateral_scratch, uint8_t *out, int width, int height, float sigma_s,
-                                float sigma_r, float detail, int op, const float *metrics, float gamma, float intensity,
+int tdb_bilateral_slice_tonemap(const float *rgb, int lab_input, const void *bilateral_scratch, uint8_t *out, int width, int height,
+                                float sigma_s, float sigma_r, float detail, int op, const float *metrics, float gamma, float intensity,
                                 float light_adapt, float vibrance, const float *matrix, int transform, tdb_stream_t stream) {
   TDB_REQUIRE(rgb && out && bilateral_scratch, "slice_tonemap: null pointer");
   TDB_REQUIRE(width > 0 && height > 0 && sigma_r > 0.0f && sigma_s > 0.0f, "slice_tonemap: invalid dimensions or sigmas");
@@ -255,8 +256,9 @@ int tdb_bilateral_slice_tonemap(const float *rgb, const void *bilateral_scratch,
   const bil::GridDims g = bil::grid_dims(width, height, sigma_s, sigma_r);
   // scratch layout of bilateral.cu: [splatted grid][blurred grid]
   const float *blurred = static_cast<const float *>(bilateral_scratch) + (size_t)g.x * g.y * g.z;
-  return launch_tonemap<true>(rgb, out, width, height, a, SliceArgs{blurred, g, sigma_s, sigma_r, detail}, as_stream(stream),
-                              "bilateral_slice_tonemap");
+  const SliceArgs sl{blurred, g, sigma_s, sigma_r, detail};
+  if (lab_input) return launch_tonemap<2>(rgb, out, width, height, a, sl, as_stream(stream), "bilateral_slice_tonemap");
+  return launch_tonemap<1>(rgb, out, width, height, a, sl, as_stream(stream), "bilateral_slice_tonemap");
 }
 
 }  // extern "C"

@@ -431,8 +431,8 @@ struct NormArgs {
   float *out;
   int width, height, channels, K, stride;
   float win[32];
-  // kSplat: the Lab L of the denoised colour is stored as well (4 B/px): it is what the bilateral grid is built from
-  // (Bilateral.process_rgb's first step), so that stage does not read the image again
+  // kSplat: the denoised colour leaves as Lab, and its L is stored once more as a plane (4 B/px): it is what the bilateral grid
+  // is built from (Bilateral.process_rgb's first step), so that stage does not read the image again
   float *lum_out;
 };
 
@@ -460,8 +460,15 @@ __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a)
         const rgb_t c{__ldg(a.rgb + 3 * i), __ldg(a.rgb + 3 * i + 1), __ldg(a.rgb + 3 * i + 2)};
         r = pub::with_luminance(c, expf(l));
       }
-      a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
-      if (kSplat) a.lum_out[i] = pub::luminance(r);
+      if (kSplat) {
+        // the bilateral stage follows: hand it rgb_to_lab(r) instead of r (r is inside [0,1]^3, so Lab L is compute_luminance(r),
+        // what the grid is built from, and the slice needs exactly this Lab for its modify_luminance): one conversion, not three
+        const rgb_t lab = pub::rgb_to_lab(r);
+        a.out[3 * i] = lab.x, a.out[3 * i + 1] = lab.y, a.out[3 * i + 2] = lab.z;
+        a.lum_out[i] = fmaxf(0.0f, lab.x);
+      } else {
+        a.out[3 * i] = r.x, a.out[3 * i + 1] = r.y, a.out[3 * i + 2] = r.z;
+      }
     } else {
       for (int ch = 0; ch < a.channels; ch++) a.out[i * a.channels + ch] = __ldg(a.acc + i * a.channels + ch) / (mask + kEps);
     }

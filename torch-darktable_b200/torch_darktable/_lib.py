@@ -71,8 +71,8 @@ _SIGNATURES = {
   'tdb_postprocess_deferred': (_I, [_P, _P, _P, _I, _I, _U32, _I, _I, _P, _I, _I, _P, _F, _P, _P, _P]),
   'tdb_frame_prepare': (_I, [_P, _P, _P, _I, _I, _U32, _P, _P, _F, _P]),
   'tdb_wiener_log_luminance_fused': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _F, _F, _P]),
-  'tdb_metrics_sliced': (_I, [_P, _P, _I, _I, _F, _F, _F, _I, _F, _P, _I, _I, _P, _F, _P, _P]),
-  'tdb_bilateral_slice_tonemap': (_I, [_P, _P, _P, _I, _I, _F, _F, _F, _I, _P, _F, _F, _F, _F, _P, _I, _P]),
+  'tdb_metrics_sliced': (_I, [_P, _I, _P, _I, _I, _F, _F, _F, _I, _F, _P, _I, _I, _P, _F, _P, _P]),
+  'tdb_bilateral_slice_tonemap': (_I, [_P, _I, _P, _P, _I, _I, _F, _F, _F, _I, _P, _F, _F, _F, _F, _P, _I, _P]),
   'tdb_bilateral_grid_rgb': (_I, [_P, _P, _I, _I, _F, _F, _P]),
 }
 

@@ -742,7 +742,8 @@ class FramePipeline:
     return out
 
   def denoise(self, wiener: 'Wiener', rgb: torch.Tensor, noise: float, prepared: bool, bilateral: 'Bilateral | None', eps: float = 1e-4):
-    """Wiener.process_log_luminance; with `bilateral` the blurred grid of the result is built in its scratch on the way.
+    """Wiener.process_log_luminance; with `bilateral` the blurred grid of the result is built in its scratch on the way and the
+    result is returned as Lab (rgb_to_lab), to be passed on with lab_input=True.
     prepared: `rgb` is what `prepare(..., wiener)` returned (the Lab (a, b) plane)."""
     if prepared:
       _require(rgb.is_cuda and rgb.dtype == torch.float32 and rgb.is_contiguous() and rgb.shape == (self._height, self._width, 2),
@@ -765,23 +766,24 @@ class FramePipeline:
                                        bilateral._sigma_r, self._s()))
 
   def metrics(self, rgb: torch.Tensor, bilateral: 'Bilateral | None', detail: float, first: bool, last: bool,
-              prev_metrics: torch.Tensor | None, moving_average: float, metrics_out: torch.Tensor, stride: int = 8, min_gray: float = 1e-4):
+              prev_metrics: torch.Tensor | None, moving_average: float, metrics_out: torch.Tensor, stride: int = 8, min_gray: float = 1e-4,
+              lab_input: bool = False):
     _rgb_image(rgb)
     grid = bilateral._grid_scratch() if bilateral is not None else None
     ss, sr = (bilateral._sigma_s, bilateral._sigma_r) if bilateral is not None else (1.0, 1.0)
     with torch.cuda.device(self._device):
-      check(lib.tdb_metrics_sliced(_ptr(rgb), _ptr(grid), self._width, self._height, ss, sr, float(detail), int(stride), float(min_gray),
+      check(lib.tdb_metrics_sliced(_ptr(rgb), int(lab_input), _ptr(grid), self._width, self._height, ss, sr, float(detail), int(stride), float(min_gray),
                                    _ptr(self._state), int(first), int(last), _ptr(prev_metrics), float(moving_average), _ptr(metrics_out),
                                    self._s()))
 
   def slice_tonemap(self, rgb: torch.Tensor, bilateral: 'Bilateral', detail: float, op: str, metrics: torch.Tensor | None, params,
-                    matrix: torch.Tensor | None = None, transform: str = 'none') -> torch.Tensor:
+                    matrix: torch.Tensor | None = None, transform: str = 'none', lab_input: bool = False) -> torch.Tensor:
     _rgb_image(rgb)
     h, w = self._height, self._width
     swap = transform in ('rotate_90', 'rotate_270', 'transpose')
     out = torch.empty((w, h, 3) if swap else (h, w, 3), dtype=torch.uint8, device=rgb.device)
     with torch.cuda.device(self._device):
-      check(lib.tdb_bilateral_slice_tonemap(_ptr(rgb), _ptr(bilateral._grid_scratch()), _ptr(out), w, h, bilateral._sigma_s,
+      check(lib.tdb_bilateral_slice_tonemap(_ptr(rgb), int(lab_input), _ptr(bilateral._grid_scratch()), _ptr(out), w, h, bilateral._sigma_s,
                                             bilateral._sigma_r, float(detail), _TM[op], _ptr(None if op == 'aces' else metrics), params.gamma,
                                             params.intensity, params.light_adapt, params.vibrance, _ptr(matrix), _TF[transform], self._s()))
     return out

@@ -267,10 +267,11 @@ class ImageProcessor:
       bil = self._bilateral_for(i) if s.enable_bilateral else None
       rgb = frame.prepare(image, ratio, self.bounds, wiener)
       if wiener is not None:
-        rgb = frame.denoise(wiener, rgb, s.denoise, True, bil)
+        rgb = frame.denoise(wiener, rgb, s.denoise, True, bil)  # Lab if the bilateral stage follows
       elif bil is not None:
         frame.bilateral_grid(bil, rgb)
-      frame.metrics(rgb, bil, s.bilateral, i == 0, i == n - 1, prev_metrics, ma, metrics)
+      lab = wiener is not None and bil is not None
+      frame.metrics(rgb, bil, s.bilateral, i == 0, i == n - 1, prev_metrics, ma, metrics, lab_input=lab)
       images.append(rgb)
     self.metrics = metrics
 
@@ -281,7 +282,8 @@ class ImageProcessor:
     for i, (name, rgb) in enumerate(zip(names, images, strict=True)):
       tf = self._transform_for(name).name
       if s.enable_bilateral:
-        out[name] = frame.slice_tonemap(rgb, self._bilateral_for(i), s.bilateral, op, self.metrics, params, None, tf)
+        out[name] = frame.slice_tonemap(rgb, self._bilateral_for(i), s.bilateral, op, self.metrics, params, None, tf,
+                                        lab_input=s.enable_denoise)
       else:
         out[name] = extension.tonemap(rgb, op, None if op == 'aces' else self.metrics, params, None, tf)
     return out
