@@ -114,7 +114,10 @@ constexpr int kMaxAxisPx = 1024;  // pixels a CTA's columns can span along one a
 // kBY: grid rows per CTA (8, or 16 for shallow grids: less halo work, 1.41x instead of 1.69x gathered columns per output column)
 // kTables: fine grids (sigma_s < 3) look the per-pixel cell index / fraction up in per-CTA tables; for coarse grids neighbouring
 // columns are sigma_s pixels apart and the table reads would collide in the same banks, so they recompute them instead
-template <int kBY, bool kTables>
+// kS2: sigma_s == 2 exactly (every camera preset of the reference): cell c is fed by the pixels 2c - 1, 2c, 2c + 1 with weights
+// 1/2, 1, 1/2 -- no tables, no ranges, nine unrolled visits whose x / y weights are immediates (powers of two: the products are the
+// ones of the general path bit for bit)
+template <int kBY, bool kTables, bool kS2 = false>
 __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__restrict__ lum, float *__restrict__ out, int width, int height,
                                                               GridDims g, float sigma_s, float sigma_r) {
   constexpr int PY = kBY + 4;
@@ -132,14 +135,14 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
   const int xbase = max(0, (int)floorf((float)(ci0 - 1) * sigma_s) - 1), ybase = max(0, (int)floorf((float)(cj0 - 1) * sigma_s) - 1);
   const int xn = min(width - xbase, min(kMaxAxisPx, (int)((GPX + 1) * sigma_s) + 8));
   const int yn = min(height - ybase, min(kMaxAxisPx, (int)((PY + 1) * sigma_s) + 8));
-  if (kTables) {
+  if (kTables && !kS2) {
     for (int t = threadIdx.x; t < max(xn, yn); t += kThreads) {
       if (t < xn) ax_x[t] = axis_sample(xbase + t, sigma_s, g.x);
       if (t < yn) ax_y[t] = axis_sample(ybase + t, sigma_s, g.y);
     }
     __syncthreads();
   }
-  if (threadIdx.x < GPX + PY) {  // inclusive pixel range (relative to the base) of the pixels whose lower cell is c - 1 or c
+  if (!kS2 && threadIdx.x < GPX + PY) {  // inclusive pixel range (relative to the base) of the pixels whose lower cell is c - 1 or c
     const bool is_x = threadIdx.x < GPX;
     const int c = is_x ? ci0 + threadIdx.x : cj0 + (threadIdx.x - GPX);
     const int n = is_x ? xn : yn, base = is_x ? xbase : ybase, cells_n = is_x ? g.x : g.y;
@@ -163,6 +166,28 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
     float *bins = cells + lj * GPX + li;
     for (int z = 0; z < g.z; z++) bins[z * ZS] = 0.0f;
     if (i < 0 || j < 0 || i >= g.x || j >= g.y) continue;
+    if (kS2) {
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) {
+        const int y = 2 * j + dy;
+        if (y < 0 || y >= height) continue;
+        const float wy = dy == 0 ? 1.0f : 0.5f;
+        const float *row = lum + (int64_t)y * width + 2 * i;
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          if (2 * i + dx < 0 || 2 * i + dx >= width) continue;
+          const float wx = dx == 0 ? 1.0f : 0.5f;
+          const float gz = fminf(fmaxf(__ldg(row + dx) / sigma_r, 0.0f), (float)(g.z - 1));
+          const int iz = min((int)gz, g.z - 2);
+          const float fz = gz - (float)iz, az = 1.0f - fz;
+          const float w0 = wx * wy * az * contrib, w1 = wx * wy * fz * contrib;
+          float *b = bins + iz * ZS;
+          if (w0 != 0.0f) b[0] += w0;
+          if (w1 != 0.0f) b[ZS] += w1;
+        }
+      }
+      continue;
+    }
     const short2 rx = rng_x[li], ry = rng_y[lj];
     for (int ty = ry.x; ty <= ry.y; ty++) {
       const AxisSample sy = kTables ? ax_y[ty] : axis_sample(ybase + ty, sigma_s, g.y);
@@ -283,11 +308,15 @@ int bilateral_build_grid(void *scratch, const float *lum, int width, int height,
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(grid_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(grid_build_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
       cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
       attr = true;
     }
     float *blurred = static_cast<float *>(scratch) + (size_t)g.x * g.y * g.z;
-    if (g.z <= 16 && sigma_s < 3.0f) {
+    if (g.z <= 16 && sigma_s == 2.0f) {
+      grid_build_kernel<16, true, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(
+          lum, blurred, width, height, g, sigma_s, sigma_r);
+    } else if (g.z <= 16 && sigma_s < 3.0f) {
       grid_build_kernel<16, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(
           lum, blurred, width, height, g, sigma_s, sigma_r);
     } else {
