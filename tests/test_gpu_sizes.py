@@ -101,15 +101,18 @@ def test_pipeline(impl, oracle, tm, deb, tf, h, w):
 
 @pytest.mark.parametrize('post,den,bil', [(True, True, True), (True, False, True), (True, True, False), (False, True, True),
                                           (False, False, False), (True, False, False)])
-@pytest.mark.parametrize('tm,deb,pattern', [('adaptive_aces', 'rcd', 'RGGB'), ('reinhard', 'ppg', 'GRBG'), ('aces', 'bilinear', 'BGGR')])
-def test_fused_image_set_equals_stage_by_stage(post, den, bil, tm, deb, pattern):
+@pytest.mark.parametrize('tm,deb,pattern,h,w', [('adaptive_aces', 'rcd', 'RGGB', 200, 328), ('reinhard', 'ppg', 'GRBG', 200, 328),
+                                                 ('aces', 'bilinear', 'BGGR', 200, 328), ('adaptive_aces', 'rcd', 'GBRG', 202, 330),
+                                                 ('linear', 'rcd', 'RGGB', 300, 520)])
+def test_fused_image_set_equals_stage_by_stage(post, den, bil, tm, deb, pattern, h, w):
   """process_image_set (fused kernels, device-resident statistics) against the same composite written with the public stage
-  calls; three image sets of 2, 1 and 3 frames so that the set merge and the moving average are exercised."""
+  calls; three image sets of 2, 1 and 3 frames so that the set merge and the moving average are exercised.  202 x 330 has a
+  width that is not a multiple of four (every scalar fall-back: no 128-bit paths, no bulk copies, no planar RCD tiles), 300 x 520
+  is large enough for interior RCD / smoothing tiles."""
   import torch
   import torch_darktable as td
   from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
   from torch_darktable.pipeline.config import Debayer, ToneMapper
-  h, w = 200, 328
   dev = torch.device('cuda:0')
   settings = ImageProcessingSettings(enable_denoise=den, enable_bilateral=bil, postprocess=post, tone_gamma=1.5, tone_intensity=2.0,
                                      light_adapt=0.8, tone_mapping=ToneMapper[tm], vibrance=0.5, debayer=Debayer[deb], moving_average=0.3)
