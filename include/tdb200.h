@@ -243,6 +243,15 @@ int tdb_bilateral_slice_tonemap(const float *rgb, int lab_input, const void *bil
                                 float sigma_s, float sigma_r, float detail, int op, const float *metrics, float gamma,
                                 float intensity, float light_adapt, float vibrance, const float *matrix, int transform,
                                 tdb_stream_t stream);
+/* The two statistics steps for ONE FRAME SPLIT INTO ROW BANDS ACROSS GPUS (pipeline/tiled.py): the rank's padded band goes
+ * through the kernels above, but only the rows it owns, [row_lo, row_hi) of the band, may count, and the results stay raw so
+ * that the ranks can all-reduce them: raw_out = {G1 sum, G2 sum, min, max of the sampled G1 greens, min, max of every other
+ * sampled value} (row_lo a multiple of 32, row_hi a multiple of 32 or the band height); raw_sums = the six metric sums.      */
+int tdb_postprocess_deferred_band(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
+                                  int bounds_stride, int row_lo, int row_hi, float *raw_out, tdb_stream_t stream);
+int tdb_metrics_sliced_band(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s,
+                            float sigma_r, float detail, int stride, float min_gray, void *frame_state, int row_lo, int row_hi,
+                            float *raw_sums, tdb_stream_t stream);
 /* the first half of tdb_bilateral_rgb: zero + splat + blur, leaving the blurred grid in scratch                          */
 int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int height, float sigma_s, float sigma_r,
                            tdb_stream_t stream);

@@ -32,9 +32,9 @@ def make_settings(debayer='rcd', tone='adaptive_aces', ma=0.5, **kw):
   return ImageProcessingSettings(**base)
 
 
-def split_rows(packed: np.ndarray, width: int, height: int, world: int):
+def split_rows(packed: np.ndarray, width: int, height: int, world: int, align: int = 8):
   rb = width * 3 // 2
-  return [packed[y0 * rb: y1 * rb] for (y0, y1) in partition_rows(height, world)]
+  return [packed[y0 * rb: y1 * rb] for (y0, y1) in partition_rows(height, world, align)]
 
 
 def run_threads(world, make_proc, frames_rows):
@@ -163,18 +163,23 @@ def untiled_cuda(h, w, frames, settings, dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('fused', [True, False])
 @pytest.mark.parametrize('world,h,w,debayer,tone', [(2, 512, 640, 'rcd', 'adaptive_aces'), (4, 1024, 328, 'rcd', 'reinhard'),
                                                      (3, 648, 200, 'ppg', 'linear'), (8, 2048, 256, 'bilinear', 'aces')])
-def test_bands_on_one_gpu_match_untiled(world, h, w, debayer, tone):
+def test_bands_on_one_gpu_match_untiled(world, h, w, debayer, tone, fused):
+  """fused: the band runs through the fused frame kernels (band statistics + all-reduce); otherwise stage by stage (CudaOps)."""
+  from torch_darktable.pipeline.tiled import CudaOps
   dev = torch.device('cuda:0')
   frames = [synth.packed_frame(h, w, seed=50 + i) for i in range(2)]
   settings = make_settings(debayer, tone)
   want, ref = untiled_cuda(h, w, frames, settings, dev)
 
   def make_proc(col):
-    return TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, WB, col)
+    return TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, WB, col,
+                               ops=None if fused else CudaOps())
 
-  rows = [[torch.from_numpy(r.copy()).to(dev) for r in split_rows(f, w, h, world)] for f in frames]
+  align = 32 if fused else 8
+  rows = [[torch.from_numpy(r.copy()).to(dev) for r in split_rows(f, w, h, world, align)] for f in frames]
   got, proc0 = run_threads(world, make_proc, rows)
   for g, e in zip(got, want):
     assert_srgb_close(g, e, frac=5e-4)
@@ -197,7 +202,7 @@ def _nccl_worker(rank, world, port, h, w, out_dir):
     frame = synth.packed_frame(h, w, seed=93)
     proc = TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, make_settings('rcd', 'adaptive_aces', 1.0), dev, WB,
                                DistCollective())
-    own = torch.from_numpy(split_rows(frame, w, h, world)[rank].copy()).to(dev)
+    own = torch.from_numpy(split_rows(frame, w, h, world, 32)[rank].copy()).to(dev)
     np.save(os.path.join(out_dir, f'band{rank}.npy'), proc.process(own).cpu().numpy())
   finally:
     dist.destroy_process_group()

@@ -53,7 +53,7 @@ def main():
                                      light_adapt=0.8, tone_mapping=ToneMapper.adaptive_aces, vibrance=0.5, debayer=Debayer.rcd,
                                      moving_average=0.5, bil_sigma_spatial=args.sigma_s)
   proc = TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, (1.8, 1.0, 2.1), col)
-  y0, y1 = partition_rows(h, world)[rank]
+  y0, y1 = proc.owned_rows
 
   # this rank's rows of a smooth synthetic CFA (gradient + gratings + noise), packed on the device
   ys = torch.arange(y0, y1, device=dev, dtype=torch.float32).unsqueeze(1)

@@ -125,6 +125,8 @@ struct MetricsArgs {
   const float *prev_metrics;  // EMA state (device float[5]) or null
   float moving_average;
   float *metrics_out;         // device float[5], written on the last frame of a set
+  int row_lo, row_hi;         // only the samples of these image rows count (one frame split into row bands)
+  float *raw_out;             // device float[6] or null: leave the raw sums of this call here, no set merge, no finalisation
 };
 
 __global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsArgs a) {
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsA
   for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < a.nsamples; s += step) {
     const int sy = (int)(s / a.sw), sx = (int)(s - (int64_t)sy * a.sw);
     const int x = sx * a.stride, y = sy * a.stride;
+    if (y < a.row_lo || y >= a.row_hi) continue;
     const float *p = a.rgb + 3 * ((int64_t)y * a.width + x);
     rgb_t c{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
     if (a.grid) c = a.lab_input ? bil::slice_lab(a.grid, x, y, c, a.g, a.sigma_s, a.sigma_r, a.detail)
@@ -170,7 +173,10 @@ __global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsA
     if (lane == 0) sh[warp][0] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && a.raw_out) {
+    for (int k = 0; k < 6; k++) a.raw_out[k] = sh[k][0];
+    fs->ticket[1] = 0;
+  } else if (threadIdx.x == 0) {
     float sums[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -210,10 +216,11 @@ int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch_buf, in
   return check_launch("frame_prepare");
 }
 
-int tdb_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r, float detail,
-                       int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set, const float *prev_metrics,
-                       float moving_average, float *metrics_out, tdb_stream_t stream) {
-  TDB_REQUIRE(rgb && frame_state && metrics_out, "metrics_sliced: null pointer");
+static int run_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s,
+                              float sigma_r, float detail, int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set,
+                              const float *prev_metrics, float moving_average, float *metrics_out, int row_lo, int row_hi, float *raw_out,
+                              tdb_stream_t stream) {
+  TDB_REQUIRE(rgb && frame_state && (metrics_out || raw_out), "metrics_sliced: null pointer");
   TDB_REQUIRE(width > 0 && height > 0 && stride > 0, "metrics_sliced: bad arguments");
   MetricsArgs a{};
   a.rgb = rgb, a.lab_input = lab_input;
@@ -230,9 +237,24 @@ int tdb_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_sc
   a.min_gray = min_gray;
   a.state = static_cast<FrameState *>(frame_state);
   a.first_in_set = first_in_set, a.last_in_set = last_in_set, a.prev_metrics = prev_metrics, a.moving_average = moving_average;
-  a.metrics_out = metrics_out;
+  a.metrics_out = metrics_out, a.row_lo = row_lo, a.row_hi = row_hi, a.raw_out = raw_out;
   metrics_sliced_kernel<<<flat_grid(a.nsamples), kThreads, 0, as_stream(stream)>>>(a);
   return check_launch("metrics_sliced");
+}
+
+int tdb_metrics_sliced(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s, float sigma_r, float detail,
+                       int stride, float min_gray, void *frame_state, int first_in_set, int last_in_set, const float *prev_metrics,
+                       float moving_average, float *metrics_out, tdb_stream_t stream) {
+  return run_metrics_sliced(rgb, lab_input, bilateral_scratch, width, height, sigma_s, sigma_r, detail, stride, min_gray, frame_state,
+                            first_in_set, last_in_set, prev_metrics, moving_average, metrics_out, 0, height, nullptr, stream);
+}
+
+int tdb_metrics_sliced_band(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s,
+                            float sigma_r, float detail, int stride, float min_gray, void *frame_state, int row_lo, int row_hi,
+                            float *raw_sums, tdb_stream_t stream) {
+  TDB_REQUIRE(raw_sums && row_lo >= 0 && row_lo < row_hi && row_hi <= height, "metrics_sliced_band: bad arguments");
+  return run_metrics_sliced(rgb, lab_input, bilateral_scratch, width, height, sigma_s, sigma_r, detail, stride, min_gray, frame_state, 1, 1,
+                            nullptr, 1.0f, nullptr, row_lo, row_hi, raw_sums, stream);
 }
 
 }  // extern "C"

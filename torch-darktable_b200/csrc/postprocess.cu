@@ -301,6 +301,36 @@ __global__ void __launch_bounds__(kStatThreads) frame_stats_kernel(const SmoothS
   }
 }
 
+// The same partials reduced over a band of CTA rows only, left RAW (G1 sum, G2 sum, min / max of the sampled G1 greens, min / max of
+// every other sampled value): what a rank contributes when one frame is split into row bands across GPUs (pipeline/tiled.py).
+__global__ void __launch_bounds__(kStatThreads) band_stats_kernel(const float *__restrict__ partials, int ctas_x, int row_lo, int row_hi,
+                                                                  float *__restrict__ raw_out) {
+  __shared__ double dsum[2][kStatThreads / 32];
+  __shared__ float red[4][kStatThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a = 0.0, b = 0.0;
+  float v[4] = {FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX};
+  for (int i = row_lo * ctas_x + tid; i < row_hi * ctas_x; i += kStatThreads) {
+    const float2 *p = reinterpret_cast<const float2 *>(partials + 6 * i);
+    const float2 s = __ldg(p), g = __ldg(p + 1), o = __ldg(p + 2);
+    a += s.x, b += s.y;
+    v[0] = fminf(v[0], g.x), v[1] = fmaxf(v[1], g.y), v[2] = fminf(v[2], o.x), v[3] = fmaxf(v[3], o.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o);
+  v[0] = warp_min(v[0]), v[1] = warp_max(v[1]), v[2] = warp_min(v[2]), v[3] = warp_max(v[3]);
+  if (lane == 0) dsum[0][warp] = a, dsum[1][warp] = b, red[0][warp] = v[0], red[1][warp] = v[1], red[2][warp] = v[2], red[3][warp] = v[3];
+  __syncthreads();
+  if (tid == 0) {
+    a = b = 0.0;
+    for (int w = 0; w < kStatThreads / 32; w++) {
+      a += dsum[0][w], b += dsum[1][w];
+      v[0] = fminf(v[0], red[0][w]), v[1] = fmaxf(v[1], red[1][w]), v[2] = fminf(v[2], red[2][w]), v[3] = fmaxf(v[3], red[3][w]);
+    }
+    raw_out[0] = (float)a, raw_out[1] = (float)b, raw_out[2] = v[0], raw_out[3] = v[1], raw_out[4] = v[2], raw_out[5] = v[3];
+  }
+}
+
 // green sums of an image that is not smoothed (passes == 0): one CTA per 32 x 32 tile
 __global__ void __launch_bounds__(kThreads) green_sums_kernel(const float *__restrict__ in, int width, int height, uint32_t filters,
                                                               float *__restrict__ partials) {
@@ -515,6 +545,25 @@ int tdb_postprocess_deferred(const float *in, float *out, void *scratch, int wid
   if (int e = run_smoothing(in, out, img_a, img_b, width, height, filters, passes, st, &nctas, s)) return e;
   frame_stats_kernel<<<1, kStatThreads, 0, s>>>(st, (unsigned int)nctas);
   return check_launch("frame_stats");
+}
+
+int tdb_postprocess_deferred_band(const float *in, float *out, void *scratch, int width, int height, uint32_t filters, int passes,
+                                  int bounds_stride, int row_lo, int row_hi, float *raw_out, tdb_stream_t stream) {
+  TDB_REQUIRE(in && out && scratch && raw_out, "postprocess_deferred_band: null pointer");
+  TDB_REQUIRE(width > 0 && height > 0 && passes >= 1 && bounds_stride >= 1, "postprocess_deferred_band: bad arguments");
+  TDB_REQUIRE(row_lo >= 0 && row_lo < row_hi && row_hi <= height && row_lo % SH == 0 && (row_hi % SH == 0 || row_hi == height),
+              "postprocess_deferred_band: the band [%d, %d) must consist of whole %d-row tiles", row_lo, row_hi, SH);
+  cudaStream_t s = as_stream(stream);
+  const size_t nblk = (size_t)div_up(width, T) * div_up(height, T);
+  char *base = static_cast<char *>(scratch);
+  float *partials = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256));
+  float *img_a = reinterpret_cast<float *>(base + align_up(sizeof(Header), 256) + align_up(nblk * 8 * sizeof(float), 256));
+  float *img_b = img_a + (size_t)width * height * 3;
+  SmoothStats st{};
+  st.mode = 2, st.stride = bounds_stride, st.partials = partials;
+  if (int e = run_smoothing(in, out, img_a, img_b, width, height, filters, passes, st, nullptr, s)) return e;
+  band_stats_kernel<<<1, kStatThreads, 0, s>>>(partials, div_up(width, SW), row_lo / SH, div_up(row_hi, SH), raw_out);
+  return check_launch("band_stats");
 }
 
 // ---- pieces of the post-process for a frame that is split into row tiles across GPUs: the green sums of the rows a rank owns

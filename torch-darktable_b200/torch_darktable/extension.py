@@ -730,6 +730,29 @@ class FramePipeline:
                                          float(moving_average), _ptr(bounds_out), _ptr(ratio), self._s()))
     return out, ratio
 
+  def smooth_band(self, post: 'PostProcess', rgb: torch.Tensor, row_lo: int, row_hi: int):
+    """smooth_deferred for a rank's band of a frame that is split across GPUs: returns (smoothed, raw) where raw[6] = G1 sum,
+    G2 sum, min / max of the sampled G1 greens, min / max of every other sampled value over the band rows [row_lo, row_hi) only."""
+    _rgb_image(rgb)
+    out = torch.empty_like(rgb)
+    raw = torch.empty(6, dtype=torch.float32, device=rgb.device)
+    scratch = post._ensure_scratch(lib.tdb_postprocess_scratch_bytes(self._width, self._height))
+    with torch.cuda.device(self._device):
+      check(lib.tdb_postprocess_deferred_band(_ptr(rgb), _ptr(out), _ptr(scratch), self._width, self._height, self._filters,
+                                              post.color_smoothing_passes, 8, int(row_lo), int(row_hi), _ptr(raw), self._s()))
+    return out, raw
+
+  def metric_sums_band(self, rgb: torch.Tensor, bilateral: 'Bilateral | None', detail: float, row_lo: int, row_hi: int,
+                       lab_input: bool = False, stride: int = 8, min_gray: float = 1e-4) -> torch.Tensor:
+    """The six raw metric sums of the (sliced) band rows [row_lo, row_hi): what the ranks all-reduce."""
+    sums = torch.empty(6, dtype=torch.float32, device=rgb.device)
+    grid = bilateral._grid_scratch() if bilateral is not None else None
+    ss, sr = (bilateral._sigma_s, bilateral._sigma_r) if bilateral is not None else (1.0, 1.0)
+    with torch.cuda.device(self._device):
+      check(lib.tdb_metrics_sliced_band(_ptr(rgb), int(lab_input), _ptr(grid), self._width, self._height, ss, sr, float(detail), int(stride),
+                                        float(min_gray), _ptr(self._state), int(row_lo), int(row_hi), _ptr(sums), self._s()))
+    return sums
+
   def prepare(self, rgb: torch.Tensor, ratio: torch.Tensor | None, bounds: torch.Tensor, wiener: 'Wiener | None', eps: float = 1e-4):
     """green_eq_global (ratio) + normalize (bounds).  With `wiener` the result is the (H, W, 2) Lab (a, b) plane of the normalised
     colour, and its log-luminance and a cleared accumulator sit in the Wiener scratch: the input of `denoise(..., prepared=True)`."""

@@ -17,8 +17,11 @@ inherited from reference artefacts that depend on absolute positions: the RCD st
 margin at the LEFT/RIGHT borders) and bilateral grids that saturate in y (height / sigma_s > 3000), which the
 split refuses.  The Laplacian local contrast has a support of thousands of rows and is not available here.
 
-The stage calls go through an `ops` object.  `CudaOps` (the default) is the product path on libtdb200; the CPU tests inject an
-oracle-backed object so that the partitioning, the halo exchange and the reductions are exercised under gloo without a GPU.
+By default a band runs through the FUSED frame kernels of libtdb200 (include/tdb200.h "Fused frame pipeline": the statistics
+kernels have band forms that count the owned rows only and leave raw sums for the all-reduce); band boundaries and the halo are
+then multiples of 32 rows, the tile height of the smoothing kernel.  With an `ops` object the stages are called one by one:
+`CudaOps` is the stage-by-stage product path, the CPU tests inject an oracle-backed object so that the partitioning, the halo
+exchange and the reductions are exercised under gloo without a GPU.
 """
 
 from __future__ import annotations
@@ -31,6 +34,7 @@ from .config import ImageProcessingSettings, ToneMapper
 from .util import lerp
 
 ROW_ALIGN = 8
+FUSED_ALIGN = 32  # the statistics of the fused smoothing kernel come per 32-row tile
 
 
 def partition_rows(height: int, world: int, align: int = ROW_ALIGN) -> list[tuple[int, int]]:
@@ -75,8 +79,8 @@ class Band:
     return self.y0 - self.top, self.y1 + self.bottom
 
 
-def make_band(height: int, rank: int, world: int, halo: int) -> Band:
-  y0, y1 = partition_rows(height, world)[rank]
+def make_band(height: int, rank: int, world: int, halo: int, align: int = ROW_ALIGN) -> Band:
+  y0, y1 = partition_rows(height, world, align)[rank]
   if world > 1 and y1 - y0 < halo:
     raise ValueError(f'band of {y1 - y0} rows is thinner than the {halo}-row halo: use fewer ranks')
   return Band(rank, world, y0, y1, top=halo if rank > 0 else 0, bottom=halo if rank + 1 < world else 0)
@@ -200,9 +204,12 @@ class TiledFrameProcessor:
     self.width, self.height = image_size
     self.bayer_pattern, self.packed_format, self.settings, self.device = bayer_pattern, packed_format, settings, device
     self.collective = collective
+    # fused kernels unless stage objects are given (or the settings leave the fused path: no post-process smoothing)
+    self.fused = ops is None and settings.postprocess and settings.color_smoothing_passes >= 1
     self.ops = ops if ops is not None else CudaOps()
-    self.halo = halo_rows(settings)
-    self.band = make_band(self.height, collective.rank, collective.world, self.halo)
+    align = FUSED_ALIGN if self.fused else ROW_ALIGN
+    self.halo = (halo_rows(settings) + align - 1) // align * align
+    self.band = make_band(self.height, collective.rank, collective.world, self.halo, align)
     self.white_balance = torch.tensor(white_balance, dtype=torch.float32, device=device) if white_balance is not None else None
     self.bounds: torch.Tensor | None = None   # EMA state, identical on every rank
     self.metrics: torch.Tensor | None = None
@@ -227,6 +234,58 @@ class TiledFrameProcessor:
     """Rows this rank owns, out of a tensor laid out over the padded band."""
     return image[self.band.top: self.band.top + (self.band.y1 - self.band.y0)]
 
+  def _fused_objects(self, size):
+    if getattr(self, '_fused_size', None) != size:
+      from ..extension import extension
+      s = self.settings
+      self._frame = extension.FramePipeline(self.device, size[0], size[1], self.bayer_pattern.value)
+      self._post = self.td.PostProcess(self.device, size, self.bayer_pattern, color_smoothing_passes=s.color_smoothing_passes,
+                                       green_eq_local=False, green_eq_global=True)._postprocess
+      self._wiener = self.td.Wiener(self.device, size)._wiener if s.enable_denoise else None
+      self._bil = (self.td.Bilateral(self.device, size, sigma_s=s.bil_sigma_spatial, sigma_r=s.bil_sigma_luminance)._bilateral
+                   if s.enable_bilateral else None)
+      self._fused_size = size
+    return self._frame, self._post, self._wiener, self._bil
+
+  def _process_fused(self, packed: torch.Tensor, size) -> torch.Tensor:
+    """The band through the fused frame kernels; three all-gathers of six floats where the single-GPU pipeline has its barriers."""
+    from ..extension import extension
+    b, s, col = self.band, self.settings, self.collective
+    frame, post, wiener, bil = self._fused_objects(size)
+    lo, hi = b.top, b.top + (b.y1 - b.y0)  # owned rows inside the padded band
+    rgb = self.td.demosaic_packed(packed, size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
+                                  white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
+    smoothed, raw = frame.smooth_band(post, rgb, lo, hi)
+    sums = col.all_reduce(raw[0:2], 'sum')
+    mins, maxs = col.all_reduce(raw[[2, 4]], 'min'), col.all_reduce(raw[[3, 5]], 'max')
+    one = torch.ones_like(sums[0])
+    ratio = torch.where((sums[0] > 0) & (sums[1] > 0), sums[1] / sums[0], one).reshape(1)
+    # bounds of the equilibrated image: the G1 greens take the ratio (x -> max(0, x * ratio) is monotone), csrc/postprocess.cu
+    have_g1 = mins[0] <= maxs[0]
+    zero = torch.zeros_like(one)
+    lo_v = torch.where(have_g1, torch.minimum(mins[1], torch.maximum(mins[0] * ratio[0], zero)), mins[1])
+    hi_v = torch.where(have_g1, torch.maximum(maxs[1], torch.maximum(maxs[0] * ratio[0], zero)), maxs[1])
+    bounds = torch.stack([lo_v, hi_v])
+    self.bounds = lerp(self.bounds if self.bounds is not None else bounds, bounds, s.moving_average)
+
+    image = frame.prepare(smoothed, ratio, self.bounds, wiener)
+    if wiener is not None:
+      image = frame.denoise(wiener, image, s.denoise, True, bil)
+    elif bil is not None:
+      frame.bilateral_grid(bil, image)
+    lab = wiener is not None and bil is not None
+    msums = col.all_reduce(frame.metric_sums_band(image, bil, s.bilateral, lo, hi, lab_input=lab), 'sum')
+    metrics = extension.metrics_from_sums(msums)
+    self.metrics = lerp(self.metrics if self.metrics is not None else metrics, metrics, s.moving_average)
+
+    params = self.td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
+    op = _TONEMAP_OPS[s.tone_mapping]
+    if bil is not None:
+      out = frame.slice_tonemap(image, bil, s.bilateral, op, self.metrics, params, None, 'none', lab_input=lab)
+    else:
+      out = extension.tonemap(image, op, None if op == 'aces' else self.metrics, params, None, 'none')
+    return self._own(out).contiguous()
+
   def process(self, own_packed_rows: torch.Tensor) -> torch.Tensor:
     """own_packed_rows: uint8 tensor with the packed bytes of this rank's rows.  Returns the uint8 (rows, W, 3) sRGB band."""
     b, s, ops, col = self.band, self.settings, self.ops, self.collective
@@ -235,6 +294,8 @@ class TiledFrameProcessor:
     packed = col.exchange_halos(own_packed_rows, self.row_bytes, b)
     p0, p1 = b.padded
     size = (self.width, p1 - p0)
+    if self.fused:
+      return self._process_fused(packed, size)
 
     rgb = ops.demosaic(packed, size, self.bayer_pattern, self.packed_format, s, self.white_balance)
     if s.postprocess:
