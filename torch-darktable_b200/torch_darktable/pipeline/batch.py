@@ -24,11 +24,17 @@ class HostFrameRunner:
     self._s_out = torch.cuda.Stream(self.device)
     self._copied = [torch.cuda.Event() for _ in range(slots)]
     self._consumed = [torch.cuda.Event() for _ in range(slots)]
+    self._ready = [torch.cuda.Event() for _ in range(slots)]
+    self._out_done = [torch.cuda.Event() for _ in range(slots)]
+    self._results: list[torch.Tensor | None] = [None] * slots  # device results whose copy-out may still be in flight
     self._done = torch.cuda.Event()
 
   def run(self, host_frames: list[torch.Tensor], host_out: list[torch.Tensor], name: str = 'cam') -> None:
     """host_frames: pinned uint8 packed frames; host_out: pinned uint8 (H', W', 3) buffers that receive the results.
-    Returns after everything has been enqueued; call `wait()` (or synchronise the device) before reading host_out."""
+    Returns after everything has been enqueued; call `wait()` (or synchronise the device) before reading host_out.
+
+    A result tensor stays referenced in its slot until the compute stream has been ordered after its copy-out, so that the
+    caching allocator hands its memory out again in plain stream order (no record_stream bookkeeping, no allocator growth)."""
     assert len(host_frames) == len(host_out)
     caller = torch.cuda.current_stream(self.device)
     for s in (self._s_in, self._s_compute, self._s_out):
@@ -42,14 +48,17 @@ class HostFrameRunner:
         self._copied[slot].record(self._s_in)
       with torch.cuda.stream(self._s_compute):
         self._s_compute.wait_event(self._copied[slot])
+        if self._results[slot] is not None:
+          self._s_compute.wait_event(self._out_done[slot])  # the copy-out of the result this slot held has finished
+          self._results[slot] = None
         result = self.processor.process(self._in[slot], name)
         self._consumed[slot].record(self._s_compute)
-        ready = torch.cuda.Event()
-        ready.record(self._s_compute)
+        self._ready[slot].record(self._s_compute)
+        self._results[slot] = result
       with torch.cuda.stream(self._s_out):
-        self._s_out.wait_event(ready)
-        result.record_stream(self._s_out)
+        self._s_out.wait_event(self._ready[slot])
         host_out[i].copy_(result, non_blocking=True)
+        self._out_done[slot].record(self._s_out)
     self._done.record(self._s_out)
     caller.wait_event(self._done)
 
