@@ -30,6 +30,7 @@ extern "C" {
 #define TDB_EINVAL 1   /* bad argument (maps to RuntimeError/ValueError in the shim) */
 #define TDB_ECUDA 2    /* CUDA runtime error (launch failure etc.) */
 #define TDB_EUNSUPPORTED 3
+#define TDB_EJPEG 4    /* nvJPEG status != success (maps to JpegException in the shim) */
 
 #define TDB_FILTERS_RGGB 0x94949494u
 #define TDB_FILTERS_BGGR 0x16161616u
@@ -255,6 +256,29 @@ int tdb_metrics_sliced_band(const float *rgb, int lab_input, const void *bilater
 /* the first half of tdb_bilateral_rgb: zero + splat + blur, leaving the blurred grid in scratch                          */
 int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int height, float sigma_s, float sigma_r,
                            tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * JPEG output of the uint8 sRGB result.  Replaces the `Jpeg` class (extension.cpp:228-233,
+ * csrc/jpeg_encoder.cu:104-180): nvJPEG (vendor library, bound lazily with dlopen) driven stream-ordered on the
+ * caller's stream.  The enum values are the reference's (csrc/jpeg_encoder.h:6-17).
+ *   tdb_jpeg_encode    device image -> encoded stream held in the coder; *length = its size in bytes.
+ *                      Interleaved formats: (H, W, 3) with `row_pitch` bytes per row (plane_stride ignored); planar
+ *                      formats: 3 planes of (H, row_pitch) bytes, `plane_stride` bytes apart.  quality 1..100,
+ *                      optimised Huffman tables always on (jpeg_encoder.cu:119).
+ *   tdb_jpeg_retrieve  copies the stream into HOST memory (synchronises `stream`, as the reference does).          */
+#define TDB_JPEG_BGR 0
+#define TDB_JPEG_RGB 1
+#define TDB_JPEG_BGRI 2
+#define TDB_JPEG_RGBI 3
+#define TDB_JPEG_CSS_444 0
+#define TDB_JPEG_CSS_422 1
+#define TDB_JPEG_CSS_GRAY 2
+int tdb_jpeg_available(void);
+int tdb_jpeg_create(void **coder);
+int tdb_jpeg_destroy(void *coder);
+int tdb_jpeg_encode(void *coder, const uint8_t *image, int width, int height, int64_t row_pitch, int64_t plane_stride,
+                    int input_format, int quality, int subsampling, int progressive, size_t *length, tdb_stream_t stream);
+int tdb_jpeg_retrieve(void *coder, uint8_t *host_out, size_t capacity, size_t *length, tdb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -336,6 +336,32 @@ def mid_cases(b: Book):
         'synth': {'kind': 'rgb', 'h': h, 'w': w, 'seed': 19}}, {}, {'out': out})
 
 
+def jpeg_image(h, w, seed):
+  """uint8 sRGB-like test picture (regenerated by seed in tests/test_jpeg.py)."""
+  return np.floor(synth.scene_rgb(h, w, seed) ** (1 / 2.2) * 255.0 + 0.5).clip(0, 255).astype(np.uint8)
+
+
+JPEG_CASES = [  # (tag, input_format, quality, subsampling, progressive)
+  ('rgbi_q94_422', 'RGBI', 94, 'CSS_422', False),
+  ('rgbi_q80_444_prog', 'RGBI', 80, 'CSS_444', True),
+  ('bgri_q94_422', 'BGRI', 94, 'CSS_422', False),
+  ('rgb_planar_q90_gray', 'RGB', 90, 'CSS_GRAY', False),
+  ('bgr_planar_q60_444', 'BGR', 60, 'CSS_444', False),
+]
+
+
+def jpeg_cases(b: Book):
+  """Streams of the reference's `Jpeg.encode` (same nvJPEG library, so the new binding must reproduce them byte for byte)."""
+  h, w = 120, 176
+  img = jpeg_image(h, w, 23)
+  coder = td.Jpeg()
+  for tag, fmt, quality, css, prog in JPEG_CASES:
+    x = cuda(img if fmt.endswith('I') else np.ascontiguousarray(img.transpose(2, 0, 1)))
+    out = coder.encode(x, quality=quality, input_format=td.jpeg.InputFormat[fmt], subsampling=td.jpeg.Subsampling[css], progressive=prog)
+    b.add(f'jpeg_{tag}', 'jpeg', {'input_format': fmt, 'quality': quality, 'subsampling': css, 'progressive': prog,
+          'synth': {'kind': 'jpeg_image', 'h': h, 'w': w, 'seed': 23}}, {}, {'out': out})
+
+
 def main():
   out_dir = Path(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/golden')
   out_dir.mkdir(parents=True, exist_ok=True)
@@ -347,6 +373,7 @@ def main():
     'filters': [wiener_cases, local_contrast_cases],
     'pipeline': [pipeline_cases],
     'mid': [mid_cases],
+    'jpeg': [jpeg_cases],
   }
   only = sys.argv[2].split(',') if len(sys.argv) > 2 else list(groups)
   errors = []

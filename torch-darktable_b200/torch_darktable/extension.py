@@ -14,7 +14,7 @@ Differences from the reference binding, all deliberate:
   * `color_transform_3x3` works on ordinary device tensors (the reference dereferences the device pointer on the host);
   * extra fused entry points used by the pipeline: unpack12_wb, demosaic_packed, wiener_log_luminance, bilateral_rgb,
     normalize, lerp, tonemap (with optional 3x3 matrix and output transform).
-JPEG encoding (nvJPEG) is outside the hot path; the names exist so that importing the package works, `encode` raises.
+`Jpeg` drives nvJPEG (a vendor library, loaded lazily by libtdb200) stream-ordered on the uint8 result of the tone map.
 """
 
 from __future__ import annotations
@@ -39,27 +39,78 @@ class BayerPattern(enum.Enum):
 
 
 class JpegInputFormat(enum.IntEnum):
-  BGR = 4
-  RGB = 3
-  BGRI = 6
-  RGBI = 5
+  """Values of the reference's `enum class JpegInputFormat` (csrc/jpeg_encoder.h:6-11), not nvJPEG's."""
+
+  BGR = 0
+  RGB = 1
+  BGRI = 2
+  RGBI = 3
 
 
 class JpegSubsampling(enum.IntEnum):
+  """csrc/jpeg_encoder.h:13-17."""
+
   CSS_444 = 0
   CSS_422 = 1
-  CSS_GRAY = 6
+  CSS_GRAY = 2
 
 
 class JpegException(Exception):
-  pass
+  """nvJPEG reported an error: "<call>, nvjpeg error <code>: <text>" (csrc/jpeg_encoder.cu:84-88)."""
 
 
 class Jpeg:
-  """Out of scope (vendor library after the sRGB output); kept so that `torch_darktable.jpeg` imports."""
+  """nvJPEG encoder object (extension.cpp:228-233, csrc/jpeg_encoder.cu:104-180): `encode` returns the JPEG stream as a CPU
+  uint8 tensor.  The encoder runs on torch's current stream of the image's device and reads the image in place through its
+  strides (rows need not be dense), so the transformed uint8 result of the tone map feeds it without a copy."""
 
-  def encode(self, image, quality, input_format, subsampling, progressive):
-    raise JpegException('JPEG encoding (nvJPEG) is not part of the B200 hot-path build')
+  def __init__(self):
+    handle = C.c_void_p()
+    self._handle = None
+    status = lib.tdb_jpeg_create(C.byref(handle))
+    if status in (3, 4):  # TDB_EUNSUPPORTED: libnvjpeg missing; TDB_EJPEG: nvJPEG refused
+      raise JpegException(_lib.last_error())
+    check(status)
+    self._handle = handle
+
+  def __del__(self):
+    handle = getattr(self, '_handle', None)
+    if handle:
+      lib.tdb_jpeg_destroy(handle)
+      self._handle = None
+
+  def encode(self, image: torch.Tensor, quality: int, input_format: int, subsampling: int, progressive: bool) -> torch.Tensor:
+    input_format, subsampling = int(input_format), int(subsampling)
+    _require(image.is_cuda, 'Input image should be on CUDA device')
+    _require(image.dtype == torch.uint8, 'Input image should be uint8')
+    if input_format not in tuple(JpegInputFormat):
+      raise RuntimeError('Invalid input format')
+    if subsampling not in tuple(JpegSubsampling):
+      raise RuntimeError('Invalid subsampling')
+    if input_format in (JpegInputFormat.BGRI, JpegInputFormat.RGBI):
+      _require(image.dim() == 3 and image.size(2) == 3, 'for interleaved (BGRI, RGBI) expected 3D tensor (H, W, C)')
+      if image.stride(2) != 1 or image.stride(1) != 3 or image.stride(0) < 3 * image.size(1):
+        image = image.contiguous()
+      height, width, pitch, plane = image.size(0), image.size(1), image.stride(0), 0
+    else:
+      _require(image.dim() == 3 and image.size(0) == 3, 'for planar (BGR, RGB) expected 3D tensor (C, H, W)')
+      if image.stride(2) != 1 or image.stride(1) < image.size(2) or image.stride(0) < image.stride(1) * image.size(1):
+        image = image.contiguous()
+      height, width, pitch, plane = image.size(1), image.size(2), image.stride(1), image.stride(0)
+    length = C.c_size_t(0)
+    with torch.cuda.device(image.device):
+      stream = _stream(image.device)
+      self._check(lib.tdb_jpeg_encode(self._handle, _ptr(image), width, height, pitch, plane, input_format, int(quality), subsampling,
+                                      1 if progressive else 0, C.byref(length), stream))
+      out = torch.empty(length.value, dtype=torch.uint8)
+      self._check(lib.tdb_jpeg_retrieve(self._handle, C.c_void_p(out.data_ptr()), length.value, C.byref(length), stream))
+    return out[: length.value]
+
+  @staticmethod
+  def _check(status: int):
+    if status == 4:  # TDB_EJPEG
+      raise JpegException(_lib.last_error())
+    check(status)
 
   def __repr__(self):
     return 'Jpeg'

@@ -1,30 +1,32 @@
-"""JPEG output.  nvJPEG encoding sits after the sRGB result and is outside the B200 hot path;
-the names exist so code importing them keeps working, `Jpeg.encode` raises JpegException."""
+"""JPEG output of the sRGB result (reference torch_darktable/jpeg.py:1-32): nvJPEG behind `extension.Jpeg`."""
 
-from enum import Enum
+from enum import IntEnum
 
 from .extension import extension
 
 JpegException = extension.JpegException
 
 
-class InputFormat(Enum):
-  BGR = extension.BGR
-  RGB = extension.RGB
-  BGRI = extension.BGRI
-  RGBI = extension.RGBI
+class InputFormat(IntEnum):
+  BGR = extension.JpegInputFormat.BGR
+  RGB = extension.JpegInputFormat.RGB
+  BGRI = extension.JpegInputFormat.BGRI
+  RGBI = extension.JpegInputFormat.RGBI
 
 
-class Subsampling(Enum):
-  CSS_444 = extension.CSS_444
-  CSS_422 = extension.CSS_422
-  CSS_GRAY = extension.CSS_GRAY
+class Subsampling(IntEnum):
+  CSS_444 = extension.JpegSubsampling.CSS_444
+  CSS_422 = extension.JpegSubsampling.CSS_422
+  CSS_GRAY = extension.JpegSubsampling.CSS_GRAY
 
 
 class Jpeg:
   def __init__(self):
-    self._coder = extension.Jpeg()
+    self.jpeg = extension.Jpeg()
 
-  def encode(self, image, quality: int = 94, input_format: InputFormat = InputFormat.RGBI,
-             subsampling: Subsampling = Subsampling.CSS_422, progressive: bool = False):
-    return self._coder.encode(image, quality, input_format.value, subsampling.value, progressive)
+  def encode(self, image, quality=94, input_format=InputFormat.RGBI, subsampling=Subsampling.CSS_422, progressive=False):
+    """(H, W, 3) / (3, H, W) uint8 CUDA tensor -> 1-D uint8 CPU tensor holding the JPEG stream."""
+    return self.jpeg.encode(image, quality, int(input_format), int(subsampling), progressive)
+
+
+__all__ = ['InputFormat', 'Jpeg', 'JpegException', 'Subsampling']
