@@ -11,7 +11,7 @@ HARNESS = r'''
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
-#include "fft32.cuh"
+#include "fft_quad.cuh"
 using namespace tdb::fft;
 template <int N> double check() {
   double err = 0;
@@ -33,7 +33,46 @@ template <int N> double check() {
   }
   return err;
 }
-int main() { printf("%.3e %.3e\n", check<32>(), check<16>()); return 0; }
+// the four-lane 32-point transform of fft_quad.cuh on four emulated lanes
+double check_quad() {
+  cpx tw[32];
+  make_quad_twiddles(tw);
+  double err = 0;
+  for (int trial = 0; trial < 20; trial++) {
+    float x_re[32], x_im[32], re[4][8], im[4][8];
+    for (int n = 0; n < 32; n++) x_re[n] = rand() / (float)RAND_MAX - 0.5f, x_im[n] = rand() / (float)RAND_MAX - 0.5f;
+    for (int j = 0; j < 4; j++)
+      for (int m = 0; m < 8; m++) re[j][m] = x_re[4 * m + j], im[j][m] = x_im[4 * m + j];
+    auto exchange = [&](int mask, void (*fn)(float &, float &, float, float, int)) {
+      float pr[4][8], pi[4][8];
+      for (int j = 0; j < 4; j++)
+        for (int p = 0; p < 8; p++) pr[j][p] = re[j ^ mask][p], pi[j][p] = im[j ^ mask][p];
+      for (int j = 0; j < 4; j++)
+        for (int p = 0; p < 8; p++) fn(re[j][p], im[j][p], pr[j][p], pi[j][p], j);
+    };
+    for (int j = 0; j < 4; j++) quad_fwd_local(re[j], im[j], tw + 8 * j);
+    exchange(2, quad_fwd_a);
+    exchange(1, quad_fwd_b);
+    for (int k = 0; k < 32; k++) {
+      double sr = 0, si = 0;
+      for (int n = 0; n < 32; n++) {
+        const double a = -2 * M_PI * k * n / 32;
+        sr += x_re[n] * cos(a) - x_im[n] * sin(a), si += x_re[n] * sin(a) + x_im[n] * cos(a);
+      }
+      const int p = quad_reg_of(k), j = quad_lane_of(k);
+      if (quad_freq(p, j) != k) return 1.0;
+      err = fmax(err, fmax(fabs(sr - re[j][p]), fabs(si - im[j][p])));
+    }
+    exchange(1, quad_inv_b);
+    exchange(2, quad_inv_a);
+    for (int j = 0; j < 4; j++) quad_inv_local(re[j], im[j], tw + 8 * j);
+    for (int j = 0; j < 4; j++)
+      for (int m = 0; m < 8; m++)
+        err = fmax(err, fmax(fabs(re[j][m] / 32 - x_re[4 * m + j]), fabs(im[j][m] / 32 - x_im[4 * m + j])));
+  }
+  return err;
+}
+int main() { printf("%.3e %.3e %.3e %.3e\n", check<32>(), check<16>(), check<8>(), check_quad()); return 0; }
 '''
 
 
@@ -43,5 +82,6 @@ def test_fft32_matches_dft(tmp_path):
   exe = tmp_path / 'fft_harness'
   subprocess.run(['g++', '-std=c++17', '-O2', '-ffp-contract=off', '-I', str(ROOT / 'torch-darktable_b200' / 'csrc'), str(src), '-o', str(exe)],
                  check=True)
-  e32, e16 = map(float, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
-  assert e32 < 2e-6 and e16 < 1e-6, (e32, e16)
+  e32, e16, e8, equad = map(float, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+  assert e32 < 2e-6 and e16 < 1e-6 and e8 < 1e-6, (e32, e16, e8)
+  assert equad < 2e-6, equad  # fft_quad.cuh: 8-point register FFTs + two exchange stages across four lanes

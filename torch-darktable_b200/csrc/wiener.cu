@@ -15,9 +15,11 @@
 //   instead of being accumulated with atomics; the accumulator has no padding.
 // No process-global device state: windows and sigmas travel as kernel arguments.
 #include <cmath>
+#include <cstdlib>
 
 #include "bilateral.cuh"
 #include "fft32.cuh"
+#include "fft_quad.cuh"
 #include "wiener_layout.cuh"
 
 namespace tdb {
@@ -242,6 +244,35 @@ __global__ void __launch_bounds__(kThreads) wiener_tile_kernel(const WienerArgs 
   }
 }
 
+// Wiener shrinkage of the two real tiles packed as z = a + i b  (apply_gain: denoise.cu:181-185), in place on the spectrum held
+// as (lane = ky in some order, register p = kx = brev(p)); `partner` = the lane that holds -ky.
+// With M = conj(Z(-k)):  A = (Z + M)/2, iB = (Z - M)/2, |A|^2 = (sr^2 + di^2)/4, |B|^2 = (si^2 + dr^2)/4 where
+// s = Z + Z(-k), d = Z - Z(-k) componentwise; shrunk Z' = gA A + i gB B.  The Hermitian pair {(ky, kx), (-ky, -kx)} shares one gain
+// evaluation: lane ky computes both shrunk bins and hands the mirrored one to lane -ky.  The scale 1/K^2 of the two inverse
+// transforms is folded into the gain numerators (kq = 1/(2 K^2) against the factor 2 of s and d).
+__device__ __forceinline__ void wiener_gains(float (&re)[32], float (&im)[32], int partner, float sg) {
+  constexpr int K = 32;
+  constexpr float kq = 1.0f / (2.0f * K * K);
+  const float n0 = kq * (kEps - sg * sg);
+#pragma unroll
+  for (int p = 0; p < K; p++) {
+    const int q = fft::brev<K>((K - fft::brev<K>(p)) & (K - 1));  // register holding -kx
+    if (q < p) continue;                                           // written by the exchange below
+    const float zr = re[p], zi = im[p];
+    const float mr = __shfl_sync(0xffffffffu, re[q], partner), mi = __shfl_sync(0xffffffffu, im[q], partner);
+    const float sr = zr + mr, dr = zr - mr, si = zi + mi, di = zi - mi;
+    const float qa = fmaf(sr, sr, di * di), qb = fmaf(si, si, dr * dr);
+    const float ga = __fdividef(fmaxf(fmaf(qa, 0.25f * kq, n0), 0.0f), fmaf(qa, 0.25f, kEps));
+    const float gb = __fdividef(fmaxf(fmaf(qb, 0.25f * kq, n0), 0.0f), fmaf(qb, 0.25f, kEps));
+    const float t0 = ga * sr, t1 = gb * dr, t2 = ga * di, t3 = gb * si;
+    re[p] = t0 + t1, im[p] = t2 + t3;
+    if (q != p) {  // the mirrored bin (-ky, -kx) lives in the partner lane's register q
+      re[q] = __shfl_sync(0xffffffffu, t0 - t1, partner);
+      im[q] = __shfl_sync(0xffffffffu, t3 - t2, partner);
+    }
+  }
+}
+
 // ---- K = 32 fast path ------------------------------------------------------------------------------------------------
 // Same warp = tile-pair organisation, rebuilt around instruction count (the v1 kernel above executed about 6400 warp
 // instructions per tile pair, half of them integer address arithmetic; ncu: profiles/r01_wiener_tile_v1_sass_hist.txt):
@@ -357,33 +388,7 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
     }
     fft::fft_fwd<K>(re, im);  // along x: register p holds kx = brev(p)
 
-    // Wiener shrinkage of the two real tiles packed as z = a + i b  (apply_gain: denoise.cu:181-185).
-    // With M = conj(Z(-k)):  A = (Z + M)/2, iB = (Z - M)/2, |A|^2 = (sr^2 + di^2)/4, |B|^2 = (si^2 + dr^2)/4 where
-    // s = Z + Z(-k), d = Z - Z(-k) componentwise; shrunk Z' = gA A + i gB B.  Scale kq = 1/(2 K^2) folded in.
-    {
-      const float sg = a.sigmas ? __ldg(a.sigmas + ch) : a.sigma_value;
-      constexpr float kq = 1.0f / (2.0f * K * K);
-      const float n0 = kq * (kEps - sg * sg);
-#pragma unroll
-      for (int p = 0; p < K; p++) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int q = fft::brev<K>((K - fft::brev<K>(p)) & (K - 1));  // register holding -kx
-        if (q < p) continue;                                           // written by the exchange below
-        const float zr = re[p], zi = im[p];
-        const float mr = __shfl_sync(0xffffffffu, re[q], partner), mi = __shfl_sync(0xffffffffu, im[q], partner);
-        const float sr = zr + mr, dr = zr - mr, si = zi + mi, di = zi - mi;
-        const float qa = fmaf(sr, sr, di * di), qb = fmaf(si, si, dr * dr);
-        const float ga = __fdividef(fmaxf(fmaf(qa, 0.25f * kq, n0), 0.0f), fmaf(qa, 0.25f, kEps));
-        const float gb = __fdividef(fmaxf(fmaf(qb, 0.25f * kq, n0), 0.0f), fmaf(qb, 0.25f, kEps));
-        const float t0 = ga * sr, t1 = gb * dr, t2 = ga * di, t3 = gb * si;
-        re[p] = t0 + t1, im[p] = t2 + t3;
-        if (q != p) {  // the mirrored bin (-ky, -kx) lives in the partner lane's register q
-          re[q] = __shfl_sync(0xffffffffu, t0 - t1, partner);
-          im[q] = __shfl_sync(0xffffffffu, t3 - t2, partner);
-        }
-      }
-    }
+    wiener_gains(re, im, partner, a.sigmas ? __ldg(a.sigmas + ch) : a.sigma_value);
 
     fft::fft_inv<K>(re, im);  // along x: register = x
     __syncwarp();
@@ -423,6 +428,214 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
     }
   }
 }
+
+// ---- K = 32, stride 8, one channel: column transforms shared between overlapping tiles -----------------------------------
+// wiener32_kernel runs four 32-point transform passes per tile pair although the four tiles that overlap horizontally apply the
+// SAME windowed column transform to the columns they share.  Here tiles are paired VERTICALLY (tile rows oy and oy + 8 as the real
+// and the imaginary part), so the column spectrum U_x[ky] = FFT_r(w_r (v[oy + r][x] + i v[oy + 8 + r][x])) depends on the image
+// column x alone and is computed once per column and tile-row pair.  The window is separable (window.h:18-43) and the tile mean
+// comes out in the frequency domain: with mu = mean_a + i mean_b and What = FFT(w),
+//     Z[ky][kx] = FFT_c( w_c (U_{ox+c}[ky] - mu What[ky]) ),
+// the shrinkage is the one of wiener32_kernel, and the inverse column transform is linear, so the four tiles covering a column
+// add up in the frequency domain first:
+//     C_x[ky] += w_c (IFFT_kx(Z')[c] + mu What[ky] w_c / 32),      out[oy + r][x] = w_r IFFT_ky(C_x)[r]
+// (real part: tile row oy, imaginary part: tile row oy + 8).  Per tile pair: 8 + 32 + 32 + 8 one-dimensional transforms instead of
+// 128, 2.5 instead of 16 loads and 4 instead of 16 atomics per pixel.
+// A CTA walks along a tile-row pair in steps of eight tile pairs (one per warp): spectra and accumulators of the 88 columns those
+// tiles touch live in shared memory ([column][36] float2: conflict-free for the column phase, 4 lanes x 8 registers per column, and
+// for the row phase, lane = frequency); the 24 columns shared with the next step are carried over.  Column transforms use four
+// lanes per column (fft_quad.cuh) so that the 64 new columns of a step occupy all 256 threads.  The work is split statically: every
+// CTA gets the same number of steps of the linearised (tile-row pair, step) sequence -- all steps cost the same, reflecting loads
+// and bounds-checked atomics included, so no interior / border split is needed.
+namespace shr {
+
+constexpr int K = 32, ST = 8;
+constexpr int TPS = kWarps;          // tile pairs per step
+constexpr int NEWC = TPS * ST;       // 64 new columns per step
+constexpr int CARRY = K - ST;        // 24 columns shared with the next step
+constexpr int BUFC = NEWC + CARRY;   // 88
+constexpr int LD = 36;               // float2 per column; = 4 (mod 16): the 16 lanes of a half-warp (4 columns x 4 quarters) hit 16 banks
+constexpr int kSmemBytes = (2 * BUFC * LD + BUFC + 32) * (int)sizeof(float2);
+
+struct Args {
+  const float *in;      // (H, W)
+  float *acc;           // (H, W), zeroed by the caller
+  const float *sigmas;  // device float[1] or null
+  float sigma_value;
+  int width, height;
+  int n_tx;             // tiles per row that touch the image: ox = -24 + 8 t
+  int steps_per_row, total_steps;
+  float win[32];        // 1-D window
+  float w2[32];         // win^2 / 32
+  fft::cpx what[32];    // FFT of the window
+  fft::cpx tw[32];      // fft_quad twiddles
+};
+
+__global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args a) {
+  extern __shared__ float2 s_shr[];
+  float2 *spec = s_shr, *accu = s_shr + BUFC * LD, *csum = accu + BUFC * LD, *twt = csum + BUFC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = a.width, H = a.height;
+  // column phase: lane = (column of the chunk, quarter); row phase: lane = position inside a column = frequency quad_freq(p, j)
+  const int cj = lane & 3, cx = lane >> 2;
+  const int ky = fft::quad_freq(lane >> 2, lane & 3);
+  const int nky = (K - ky) & (K - 1);
+  const int partner = fft::quad_reg_of(nky) * 4 + fft::quad_lane_of(nky);
+  const float whx = a.what[ky].x, why = a.what[ky].y;
+  if (tid < 32) twt[tid] = make_float2(a.tw[tid].x, a.tw[tid].y);
+  const float2 *twl = twt + 8 * cj;
+  const float sg = a.sigmas ? __ldg(a.sigmas) : a.sigma_value;
+
+  const int L0 = (int)((int64_t)blockIdx.x * a.total_steps / gridDim.x), L1 = (int)((int64_t)(blockIdx.x + 1) * a.total_steps / gridDim.x);
+  for (int L = L0; L < L1; L++) {
+    const int P = L / a.steps_per_row, k = L - P * a.steps_per_row;
+    const bool first = L == L0 || k == 0, last = L == L1 - 1 || k == a.steps_per_row - 1;
+    const int oy = -CARRY + 2 * ST * P;   // tile row of the real part; the imaginary part is the tile row oy + 8
+    const int cb = -CARRY + NEWC * k;     // image column of buffer column 0; tile pair w of this step starts at cb + 8 w
+
+    // ---- column phase: spectra of the new columns -------------------------------------------------------------------------
+    // (every warp runs the same instruction stream: chunks beyond the buffer are computed on a clamped column and not stored, so
+    // the shuffles sit in uniform control flow)
+    if (first)
+      for (int i = tid; i < BUFC * LD; i += kThreads) accu[i] = make_float2(0.0f, 0.0f);
+    auto column_forward = [&](int c0) {
+      const bool valid = c0 < BUFC;
+      const int bc = (valid ? c0 : 0) + cx;
+      const float *col = a.in + reflect_index(cb + bc, W);
+      float v[10];
+#pragma unroll
+      for (int m = 0; m < 10; m++) v[m] = __ldg(col + (int64_t)reflect_index(oy + 4 * m + cj, H) * W);
+      float re[8], im[8], sa = 0.0f, sb = 0.0f;
+#pragma unroll
+      for (int m = 0; m < 8; m++) {
+        const float wm = a.win[4 * m + cj];
+        sa += v[m], sb += v[m + 2];
+        re[m] = v[m] * wm, im[m] = v[m + 2] * wm;
+      }
+      sa += __shfl_xor_sync(0xffffffffu, sa, 1), sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+      sa += __shfl_xor_sync(0xffffffffu, sa, 2), sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      fft::quad_fwd_local(re, im, twl);
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const float pr = __shfl_xor_sync(0xffffffffu, re[p], 2), pi = __shfl_xor_sync(0xffffffffu, im[p], 2);
+        fft::quad_fwd_a(re[p], im[p], pr, pi, cj);
+      }
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const float pr = __shfl_xor_sync(0xffffffffu, re[p], 1), pi = __shfl_xor_sync(0xffffffffu, im[p], 1);
+        fft::quad_fwd_b(re[p], im[p], pr, pi, cj);
+      }
+      if (valid) {
+        if (cj == 0) csum[bc] = make_float2(sa, sb);
+        float2 *dst = spec + bc * LD + cj;
+#pragma unroll
+        for (int p = 0; p < 8; p++) dst[4 * p] = make_float2(re[p], im[p]);
+      }
+    };
+    column_forward((first ? 0 : CARRY) + ST * warp);
+    if (first) column_forward(NEWC + ST * warp);  // the 24 columns a step normally inherits
+    __syncthreads();
+
+    // ---- row phase: one tile pair per warp -------------------------------------------------------------------------------------
+    const bool active = TPS * k + warp < a.n_tx;  // uniform per warp
+    float re[K], im[K];
+    float q32r, q32i;
+    {  // warps without a tile (end of a tile row) run on whatever the buffer holds and skip the accumulation
+      const float2 *src = spec + (ST * warp) * LD + lane;
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        const float2 z = src[c * LD];
+        re[c] = z.x, im[c] = z.y;
+      }
+      const float2 cs = csum[ST * warp + lane];
+      const float ma = warp_sum(cs.x) * (1.0f / (K * K)), mb = warp_sum(cs.y) * (1.0f / (K * K));
+      const float qr = ma * whx - mb * why, qi = ma * why + mb * whx;  // (mean_a + i mean_b) What[ky]
+#pragma unroll
+      for (int c = 0; c < K; c++) re[c] = (re[c] - qr) * a.win[c], im[c] = (im[c] - qi) * a.win[c];
+      fft::fft_fwd<K>(re, im);  // along x: register p holds kx = brev(p)
+      wiener_gains(re, im, partner, sg);
+      fft::fft_inv<K>(re, im);  // register = column of the tile, scaled by 1 / K^2
+      q32r = qr, q32i = qi;     // a.w2 carries the 1/32
+    }
+    // the four column blocks of a tile are shared with the neighbouring warps' tiles: block j of every warp in turn
+#pragma unroll
+    for (int j = 0; j < K / ST; j++) {
+      if (active) {
+        float2 *dst = accu + (ST * warp + ST * j) * LD + lane;
+#pragma unroll
+        for (int c = 0; c < ST; c++) {
+          float2 z = dst[c * LD];
+          z.x = fmaf(a.win[ST * j + c], re[ST * j + c], fmaf(a.w2[ST * j + c], q32r, z.x));
+          z.y = fmaf(a.win[ST * j + c], im[ST * j + c], fmaf(a.w2[ST * j + c], q32i, z.y));
+          dst[c * LD] = z;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- column phase back: the columns no later tile touches ---------------------------------------------------------------------
+    auto column_back = [&](int c0) {
+      const bool valid = c0 < BUFC;
+      const int bc = (valid ? c0 : 0) + cx;
+      const float2 *src = accu + bc * LD + cj;
+      float cr[8], ci[8];
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const float2 z = src[4 * p];
+        cr[p] = z.x, ci[p] = z.y;
+      }
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const float pr = __shfl_xor_sync(0xffffffffu, cr[p], 1), pi = __shfl_xor_sync(0xffffffffu, ci[p], 1);
+        fft::quad_inv_b(cr[p], ci[p], pr, pi, cj);
+      }
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const float pr = __shfl_xor_sync(0xffffffffu, cr[p], 2), pi = __shfl_xor_sync(0xffffffffu, ci[p], 2);
+        fft::quad_inv_a(cr[p], ci[p], pr, pi, cj);
+      }
+      fft::quad_inv_local(cr, ci, twl);  // register m = row 4 m + cj of the tile
+      const int x = cb + bc;
+      if (valid && x >= 0 && x < W) {
+        float *dst = a.acc + x;
+#pragma unroll
+        for (int m = 0; m < 10; m++) {  // rows oy + 4 m + cj: tile row oy contributes m < 8, tile row oy + 8 contributes m >= 2
+          float val = 0.0f;
+          if (m < 8) val = cr[m] * a.win[4 * m + cj];
+          if (m >= 2) val = fmaf(ci[m - 2], a.win[4 * (m - 2) + cj], val);
+          const int y = oy + 4 * m + cj;
+          if (y >= 0 && y < H) atomicAdd(dst + (int64_t)y * W, val);
+        }
+      }
+    };
+    column_back(ST * warp);
+    if (last) column_back(NEWC + ST * warp);
+    __syncthreads();
+    if (!last) {
+      // carry the 24 columns the next step shares (spectra, partial accumulators, column sums), clear the rest of the accumulators
+      constexpr int NC = CARRY * LD;  // 864 float2
+      float2 ks[(NC + kThreads - 1) / kThreads], ka[(NC + kThreads - 1) / kThreads];
+#pragma unroll
+      for (int i = 0; i < (NC + kThreads - 1) / kThreads; i++) {
+        const int e = tid + i * kThreads;
+        if (e < NC) ks[i] = spec[NEWC * LD + e], ka[i] = accu[NEWC * LD + e];
+      }
+      float2 kc = make_float2(0.0f, 0.0f);
+      if (tid < CARRY) kc = csum[NEWC + tid];
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < (NC + kThreads - 1) / kThreads; i++) {
+        const int e = tid + i * kThreads;
+        if (e < NC) spec[e] = ks[i], accu[e] = ka[i];
+      }
+      if (tid < CARRY) csum[tid] = kc;
+      for (int i = NC + tid; i < BUFC * LD; i += kThreads) accu[i] = make_float2(0.0f, 0.0f);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace shr
 
 // closed-form weight mask: sum over the overlap^2 covering tiles of (w_fft * w_interp)(x) * (w_fft * w_interp)(y)
 struct NormArgs {
@@ -498,6 +711,44 @@ void make_window(int K, float *win) {
   for (int i = K; i < 32; i++) win[i] = 0.0f;
 }
 
+// the shared-column kernel for (K = 32, stride 8, one channel), the configuration of the frame pipeline.  TDB_WIENER_SHARED=0 keeps
+// wiener32_kernel (A/B runs).
+bool use_shared_columns() {
+  static const bool on = [] {
+    const char *e = getenv("TDB_WIENER_SHARED");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
+int run_tiles_shared(const float *in, float *acc, int width, int height, const float *sigmas, float sigma_value, cudaStream_t s) {
+  shr::Args a{};
+  a.in = in, a.acc = acc, a.sigmas = sigmas, a.sigma_value = sigma_value, a.width = width, a.height = height;
+  a.n_tx = (width - 1 + shr::CARRY) / shr::ST + 1;
+  const int n_ty = (height - 1 + shr::CARRY) / shr::ST + 1;
+  a.steps_per_row = (a.n_tx + shr::TPS - 1) / shr::TPS;
+  a.total_steps = a.steps_per_row * ((n_ty + 1) / 2);
+  make_window(32, a.win);
+  for (int i = 0; i < 32; i++) a.w2[i] = a.win[i] * a.win[i] * (1.0f / 32.0f);
+  for (int k = 0; k < 32; k++) {
+    double re = 0.0, im = 0.0;
+    for (int r = 0; r < 32; r++) {
+      const double ang = -2.0 * 3.14159265358979323846 * k * r / 32.0;
+      re += a.win[r] * cos(ang), im += a.win[r] * sin(ang);
+    }
+    a.what[k] = fft::cpx{(float)re, (float)im};
+  }
+  fft::make_quad_twiddles(a.tw);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(shr::wiener32_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
+    attr = true;
+  }
+  const int grid = a.total_steps < 2 * kNumSMs ? a.total_steps : 2 * kNumSMs;
+  shr::wiener32_shared_kernel<<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  return check_launch("wiener_tiles");
+}
+
 int run_tiles(const float *in, float *acc, int width, int height, int channels, int tile, int overlap, const float *sigmas,
               float sigma_value, cudaStream_t s, bool cleared = false) {
   WienerArgs a{};
@@ -527,6 +778,7 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
     cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
     attr = true;
   }
+  if (tile == 32 && channels == 1 && a.stride == shr::ST && use_shared_columns()) return run_tiles_shared(in, acc, width, height, sigmas, sigma_value, s);
   if (tile == 32) {
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
     static bool attr32 = false;
