@@ -487,11 +487,14 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
   const float sg = a.sigmas ? __ldg(a.sigmas) : a.sigma_value;
 
   const int L0 = (int)((int64_t)blockIdx.x * a.total_steps / gridDim.x), L1 = (int)((int64_t)(blockIdx.x + 1) * a.total_steps / gridDim.x);
-  for (int L = L0; L < L1; L++) {
-    const int P = L / a.steps_per_row, k = L - P * a.steps_per_row;
+  const int w4 = 4 * W;
+  int P = L0 / a.steps_per_row, k = L0 - P * a.steps_per_row;
+  for (int L = L0; L < L1; L++, k++) {
+    if (k == a.steps_per_row) k = 0, P++;
     const bool first = L == L0 || k == 0, last = L == L1 - 1 || k == a.steps_per_row - 1;
     const int oy = -CARRY + 2 * ST * P;   // tile row of the real part; the imaginary part is the tile row oy + 8
     const int cb = -CARRY + NEWC * k;     // image column of buffer column 0; tile pair w of this step starts at cb + 8 w
+    const bool rows_inside = oy >= 0 && oy + K + ST <= H;
 
     // ---- column phase: spectra of the new columns -------------------------------------------------------------------------
     // (every warp runs the same instruction stream: chunks beyond the buffer are computed on a clamped column and not stored, so
@@ -503,8 +506,14 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
       const int bc = (valid ? c0 : 0) + cx;
       const float *col = a.in + reflect_index(cb + bc, W);
       float v[10];
+      if (rows_inside) {  // rows oy .. oy + 39 inside the image (uniform per step): no reflection, one multiply-add per row
+        const int off = (oy + cj) * W;  // element offsets fit 32 bits (check_args)
 #pragma unroll
-      for (int m = 0; m < 10; m++) v[m] = __ldg(col + (int64_t)reflect_index(oy + 4 * m + cj, H) * W);
+        for (int m = 0; m < 10; m++) v[m] = __ldg(col + (off + m * w4));
+      } else {
+#pragma unroll
+        for (int m = 0; m < 10; m++) v[m] = __ldg(col + (int64_t)reflect_index(oy + 4 * m + cj, H) * W);
+      }
       float re[8], im[8], sa = 0.0f, sb = 0.0f;
 #pragma unroll
       for (int m = 0; m < 8; m++) {
@@ -597,14 +606,26 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
       fft::quad_inv_local(cr, ci, twl);  // register m = row 4 m + cj of the tile
       const int x = cb + bc;
       if (valid && x >= 0 && x < W) {
-        float *dst = a.acc + x;
+        float wr[8];
 #pragma unroll
-        for (int m = 0; m < 10; m++) {  // rows oy + 4 m + cj: tile row oy contributes m < 8, tile row oy + 8 contributes m >= 2
-          float val = 0.0f;
-          if (m < 8) val = cr[m] * a.win[4 * m + cj];
-          if (m >= 2) val = fmaf(ci[m - 2], a.win[4 * (m - 2) + cj], val);
-          const int y = oy + 4 * m + cj;
-          if (y >= 0 && y < H) atomicAdd(dst + (int64_t)y * W, val);
+        for (int m = 0; m < 8; m++) wr[m] = a.win[4 * m + cj];
+        float val[10];  // rows oy + 4 m + cj: tile row oy contributes m < 8, tile row oy + 8 contributes m >= 2
+#pragma unroll
+        for (int m = 0; m < 10; m++) {
+          val[m] = m < 8 ? cr[m] * wr[m] : 0.0f;
+          if (m >= 2) val[m] = fmaf(ci[m - 2], wr[m - 2], val[m]);
+        }
+        float *dst = a.acc + x;
+        if (rows_inside) {
+          const int off = (oy + cj) * W;
+#pragma unroll
+          for (int m = 0; m < 10; m++) atomicAdd(dst + (off + m * w4), val[m]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 10; m++) {
+            const int y = oy + 4 * m + cj;
+            if (y >= 0 && y < H) atomicAdd(dst + (int64_t)y * W, val[m]);
+          }
         }
       }
     };
