@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_kernel(const WienerArgs 
   }
 }
 
-// ---- K = 32, stride 8, one channel: column transforms shared between overlapping tiles -----------------------------------
+// ---- K = 32, stride 8 (the default overlap 4): column transforms shared between overlapping tiles -----------------------------------
 // wiener32_kernel runs four 32-point transform passes per tile pair although the four tiles that overlap horizontally apply the
 // SAME windowed column transform to the columns they share.  Here tiles are paired VERTICALLY (tile rows oy and oy + 8 as the real
 // and the imaginary part), so the column spectrum U_x[ky] = FFT_r(w_r (v[oy + r][x] + i v[oy + 8 + r][x])) depends on the image
@@ -462,11 +462,12 @@ constexpr int LD = 36;               // float2 per column; = 4 (mod 16): the 16 
 constexpr int kSmemBytes = (2 * BUFC * LD + BUFC + 32) * (int)sizeof(float2);
 
 struct Args {
-  const float *in;      // (H, W)
-  float *acc;           // (H, W), zeroed by the caller
-  const float *sigmas;  // device float[1] or null
+  const float *in;      // (H, W, C)
+  float *acc;           // (H, W, C), zeroed by the caller
+  const float *sigmas;  // device float[C] or null
   float sigma_value;
-  int width, height;
+  int width, height, channels;
+  int n_pairs;          // tile-row pairs per channel
   int n_tx;             // tiles per row that touch the image: ox = -24 + 8 t
   int steps_per_row, total_steps;
   float win[32];        // 1-D window
@@ -488,13 +489,19 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
   const float whx = a.what[ky].x, why = a.what[ky].y;
   if (tid < 32) twt[tid] = make_float2(a.tw[tid].x, a.tw[tid].y);
   const float2 *twl = twt + 8 * cj;
-  const float sg = a.sigmas ? __ldg(a.sigmas) : a.sigma_value;
+  const int cs = a.channels, Wc = W * cs;  // channels are interleaved: element (y, x, ch) at (y * W + x) * cs + ch
 
   const int L0 = (int)((int64_t)blockIdx.x * a.total_steps / gridDim.x), L1 = (int)((int64_t)(blockIdx.x + 1) * a.total_steps / gridDim.x);
-  const int w4 = 4 * W;
-  int P = L0 / a.steps_per_row, k = L0 - P * a.steps_per_row;
+  const int w4 = 4 * Wc;
+  int P = L0 / a.steps_per_row, k = L0 - P * a.steps_per_row;  // the sequence runs over (channel, tile-row pair, step)
+  int ch = P / a.n_pairs;
+  P -= ch * a.n_pairs;
   for (int L = L0; L < L1; L++, k++) {
-    if (k == a.steps_per_row) k = 0, P++;
+    if (k == a.steps_per_row) {
+      k = 0;
+      if (++P == a.n_pairs) P = 0, ch++;
+    }
+    const float sg = a.sigmas ? __ldg(a.sigmas + ch) : a.sigma_value;
     const bool first = L == L0 || k == 0, last = L == L1 - 1 || k == a.steps_per_row - 1;
     const int oy = -CARRY + 2 * ST * P;   // tile row of the real part; the imaginary part is the tile row oy + 8
     const int cb = -CARRY + NEWC * k;     // image column of buffer column 0; tile pair w of this step starts at cb + 8 w
@@ -508,15 +515,15 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
     auto column_forward = [&](int c0) {
       const bool valid = c0 < BUFC;
       const int bc = (valid ? c0 : 0) + cx;
-      const float *col = a.in + reflect_index(cb + bc, W);
+      const float *col = a.in + (reflect_index(cb + bc, W) * cs + ch);
       float v[10];
       if (rows_inside) {  // rows oy .. oy + 39 inside the image (uniform per step): no reflection, one multiply-add per row
-        const int off = (oy + cj) * W;  // element offsets fit 32 bits (check_args)
+        const int off = (oy + cj) * Wc;  // element offsets fit 32 bits (check_args)
 #pragma unroll
         for (int m = 0; m < 10; m++) v[m] = __ldg(col + (off + m * w4));
       } else {
 #pragma unroll
-        for (int m = 0; m < 10; m++) v[m] = __ldg(col + (int64_t)reflect_index(oy + 4 * m + cj, H) * W);
+        for (int m = 0; m < 10; m++) v[m] = __ldg(col + (int64_t)reflect_index(oy + 4 * m + cj, H) * Wc);
       }
       float re[8], im[8], sa = 0.0f, sb = 0.0f;
 #pragma unroll
@@ -619,16 +626,16 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
           val[m] = m < 8 ? cr[m] * wr[m] : 0.0f;
           if (m >= 2) val[m] = fmaf(ci[m - 2], wr[m - 2], val[m]);
         }
-        float *dst = a.acc + x;
+        float *dst = a.acc + (x * cs + ch);
         if (rows_inside) {
-          const int off = (oy + cj) * W;
+          const int off = (oy + cj) * Wc;
 #pragma unroll
           for (int m = 0; m < 10; m++) atomicAdd(dst + (off + m * w4), val[m]);
         } else {
 #pragma unroll
           for (int m = 0; m < 10; m++) {
             const int y = oy + 4 * m + cj;
-            if (y >= 0 && y < H) atomicAdd(dst + (int64_t)y * W, val[m]);
+            if (y >= 0 && y < H) atomicAdd(dst + (int64_t)y * Wc, val[m]);
           }
         }
       }
@@ -736,7 +743,7 @@ void make_window(int K, float *win) {
   for (int i = K; i < 32; i++) win[i] = 0.0f;
 }
 
-// the shared-column kernel for (K = 32, stride 8, one channel), the configuration of the frame pipeline.  TDB_WIENER_SHARED=0 keeps
+// the shared-column kernel for K = 32, stride 8 (the configuration of the frame pipeline and the default of Wiener.process).  TDB_WIENER_SHARED=0 keeps
 // wiener32_kernel (A/B runs).
 bool use_shared_columns() {
   static const bool on = [] {
@@ -746,13 +753,15 @@ bool use_shared_columns() {
   return on;
 }
 
-int run_tiles_shared(const float *in, float *acc, int width, int height, const float *sigmas, float sigma_value, cudaStream_t s) {
+int run_tiles_shared(const float *in, float *acc, int width, int height, int channels, const float *sigmas, float sigma_value,
+                     cudaStream_t s) {
   shr::Args a{};
-  a.in = in, a.acc = acc, a.sigmas = sigmas, a.sigma_value = sigma_value, a.width = width, a.height = height;
+  a.in = in, a.acc = acc, a.sigmas = sigmas, a.sigma_value = sigma_value, a.width = width, a.height = height, a.channels = channels;
   a.n_tx = (width - 1 + shr::CARRY) / shr::ST + 1;
   const int n_ty = (height - 1 + shr::CARRY) / shr::ST + 1;
   a.steps_per_row = (a.n_tx + shr::TPS - 1) / shr::TPS;
-  a.total_steps = a.steps_per_row * ((n_ty + 1) / 2);
+  a.n_pairs = (n_ty + 1) / 2;
+  a.total_steps = a.steps_per_row * a.n_pairs * channels;
   make_window(32, a.win);
   for (int i = 0; i < 32; i++) a.w2[i] = a.win[i] * a.win[i] * (1.0f / 32.0f);
   for (int k = 0; k < 32; k++) {
@@ -803,7 +812,7 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
     cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
     attr = true;
   }
-  if (tile == 32 && channels == 1 && a.stride == shr::ST && use_shared_columns()) return run_tiles_shared(in, acc, width, height, sigmas, sigma_value, s);
+  if (tile == 32 && a.stride == shr::ST && use_shared_columns()) return run_tiles_shared(in, acc, width, height, channels, sigmas, sigma_value, s);
   if (tile == 32) {
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
     static bool attr32 = false;
