@@ -217,7 +217,7 @@ def run_ours(args):
     pass
   roofline = {'kernel': top['kernel'], 'bound': 'hbm', 'achieved': top['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
               'frac': top['frac'], 'traffic': traffic, 'peak_source': peak_src, 'ms_per_launch': top['ms_per_launch'],
-              'note': 'wiener_tiles is FP32-issue bound (register FFTs, 16 covering tiles per pixel), not HBM bound; see DESIGN.md'}
+              'note': 'wiener_tiles is bound by the FP32 lanes (register FFTs of 16 covering tiles per pixel, column transforms shared between tiles), not by HBM; see DESIGN.md'}
 
   # end to end through host buffers
   out_shape = (WIDTH, HEIGHT, 3)  # rotate_270 swaps the axes

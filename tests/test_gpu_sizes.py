@@ -73,6 +73,19 @@ def test_wiener(impl, oracle, k, ov, c, h, w):
   check('wiener', impl, oracle, {'sigmas': sigmas, 'tile_size': k, 'overlap_factor': ov}, {'x': x})
 
 
+# The shared-column kernel (K = 32, overlap 4; csrc/wiener.cu namespace shr) walks tile-row PAIRS in steps of eight tile pairs with
+# a static split of the step sequence over the CTAs: sides below one tile / one step, odd numbers of tile rows, sides that are
+# not multiples of the stride, frames narrower than the 88-column step buffer, and a frame large enough that CTAs start and stop
+# in the middle of a tile row (1104 steps over 296 CTAs).
+@pytest.mark.parametrize('h,w,c', [(20, 44, 1), (33, 70, 1), (33, 70, 3), (40, 64, 1), (47, 130, 3), (96, 56, 1), (121, 333, 1),
+                                   (700, 1500, 1)])
+def test_wiener_shared_columns_geometry(impl, oracle, h, w, c):
+  rng = np.random.default_rng(7)
+  x = (synth.scene_rgb(h, w, 23)[..., :c] + rng.normal(0, 0.03, size=(h, w, c))).astype(np.float32)
+  sigmas = [0.03, 0.05, 0.02][:c]
+  check('wiener', impl, oracle, {'sigmas': sigmas, 'tile_size': 32, 'overlap_factor': 4}, {'x': x})
+
+
 @pytest.mark.parametrize('h,w', SIZES)
 def test_wiener_log_luminance(impl, oracle, h, w):
   rng = np.random.default_rng(6)

@@ -9,7 +9,7 @@ CMD="python bench.py --frames 2 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:rcd3_kernel|smooth_kernel|frame_stats_kernel|prepare_kernel|wiener32_kernel|wiener_normalize_kernel|grid_build_kernel|metrics_sliced_kernel|tonemap_kernel' -s 27 -c 9 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:rcd3_kernel|smooth_kernel|frame_stats_kernel|prepare_kernel|wiener32_kernel|wiener32_shared_kernel|wiener_normalize_kernel|grid_build_kernel|metrics_sliced_kernel|tonemap_kernel' -s 27 -c 9 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
 python - <<P
 import json

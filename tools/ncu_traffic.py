@@ -2,7 +2,7 @@
   python tools/ncu_traffic.py profiles/r01_ncu_full_v7_summary.csv"""
 import csv, json, sys
 NAMES = {'rcd3_kernel': 'rcd_demosaic', 'smooth_kernel': 'color_smoothing', 'frame_stats_kernel': 'frame_stats', 'prepare_kernel': 'frame_prepare',
-         'wiener32_kernel': 'wiener_tiles', 'wiener_normalize_kernel': 'wiener_normalize_lum', 'grid_build_kernel': 'bilateral_grid_build',
+         'wiener32_kernel': 'wiener_tiles', 'wiener32_shared_kernel': 'wiener_tiles', 'wiener_normalize_kernel': 'wiener_normalize_lum', 'grid_build_kernel': 'bilateral_grid_build',
          'metrics_sliced_kernel': 'metrics_sliced', 'tonemap_kernel': 'bilateral_slice_tonemap'}
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
