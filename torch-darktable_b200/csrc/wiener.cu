@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args
   const int partner = fft::quad_reg_of(nky) * 4 + fft::quad_lane_of(nky);
   const float whx = a.what[ky].x, why = a.what[ky].y;
   if (tid < 32) twt[tid] = make_float2(a.tw[tid].x, a.tw[tid].y);
+  __syncthreads();  // the table is read by every warp's first column transform
   const float2 *twl = twt + 8 * cj;
   const int cs = a.channels, Wc = W * cs;  // channels are interleaved: element (y, x, ch) at (y * W + x) * cs + ch
 
