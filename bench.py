@@ -9,7 +9,8 @@ the `artichoke` camera settings).  Prints ONE JSON line on rank 0.
 
   value      frames already resident in HBM, CUDA-event time, max over ranks
   e2e        the same through pinned HOST buffers (H2D of every packed frame and D2H of every uint8 result inside the
-             timed region), via torch_darktable.pipeline.batch.HostFrameRunner
+             timed region), via torch_darktable.pipeline.batch.HostFrameRunner; the steps are streamed (the copy-in of a
+             step overlaps the tail of the previous one), the host waits once, inside the timed region's closing sync
   roofline   the dominant kernel, timed per launch with CUDA events on its stream (libtdb200's timing hook), against
              the measured HBM copy bandwidth of MEASURED_PEAKS.json; `stages` lists every kernel the same way
   cpu_baseline  the CPU oracle (oracle/, OpenMP on all host cores) on a bounded sample (one frame), rank 0, N=1 only
@@ -224,11 +225,11 @@ def run_ours(args):
   host_out = [torch.empty(out_shape, dtype=torch.uint8).pin_memory() for _ in range(FRAMES)]
   runner = HostFrameRunner(proc)
 
-  def step_e2e():
-    runner.run(host, host_out)
-    runner.wait()
+  def step_e2e():  # batches are streamed: the copy-in of the next step overlaps the tail of this one, one host wait at the end
+    runner.run(host, host_out, after_caller=False)
 
   e2e_ms = timed_steps(torch, dist, step_e2e, args.steps, max(args.warmup, 1), world)
+  runner.wait()
 
   if rank == 0:
     line = {

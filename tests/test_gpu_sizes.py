@@ -176,3 +176,26 @@ def test_laplacian(impl, oracle, sigma, shadows, highlights, clarity, h, w):
   (one row / column / pixel computed and replicated) run next to the ordinary ones, at every pyramid level."""
   lum = synth.scene_rgb(h, w, 31)[..., 1].copy()
   check('laplacian', impl, oracle, {'sigma': sigma, 'shadows': shadows, 'highlights': highlights, 'clarity': clarity}, {'lum': lum})
+
+
+def test_host_frame_runner_streams_batches():
+  """HostFrameRunner: pinned host frames in, pinned host results out, three streams; consecutive batches queued without a host
+  wait in between (after_caller=False) hand their slots over by events.  Every result must equal ImageProcessor.process."""
+  import torch
+  import torch_darktable as td
+  from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
+  from torch_darktable.pipeline.batch import HostFrameRunner
+  w, h = 256, 192
+  dev = torch.device('cuda:0')
+  settings = ImageProcessingSettings(moving_average=1.0)
+  make = lambda: ImageProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, (1.8, 1.0, 2.1), ImageTransform.rotate_90)
+  frames = [torch.from_numpy(synth.packed_frame(h, w, seed=40 + i)).pin_memory() for i in range(11)]
+  want = [make().process(f.to(dev), 'cam').cpu() for f in frames]
+  runner = HostFrameRunner(make(), slots=3)
+  outs = [torch.empty((w, h, 3), dtype=torch.uint8).pin_memory() for _ in frames]
+  runner.run(frames[:5], outs[:5], after_caller=False)   # 5, 4 and 2 frames: the slot rotation continues across the calls
+  runner.run(frames[5:9], outs[5:9], after_caller=False)
+  runner.run(frames[9:], outs[9:])
+  runner.wait()
+  for i, (got, ref) in enumerate(zip(outs, want)):
+    assert torch.equal(got, ref), f'frame {i} differs'

@@ -28,22 +28,30 @@ class HostFrameRunner:
     self._out_done = [torch.cuda.Event() for _ in range(slots)]
     self._results: list[torch.Tensor | None] = [None] * slots  # device results whose copy-out may still be in flight
     self._done = torch.cuda.Event()
+    self._used = [False] * slots  # slot has held a frame before (its events are recorded)
+    self._next = 0                # slot of the next frame: batches continue round robin across calls
 
-  def run(self, host_frames: list[torch.Tensor], host_out: list[torch.Tensor], name: str = 'cam') -> None:
+  def run(self, host_frames: list[torch.Tensor], host_out: list[torch.Tensor], name: str = 'cam', after_caller: bool = True) -> None:
     """host_frames: pinned uint8 packed frames; host_out: pinned uint8 (H', W', 3) buffers that receive the results.
     Returns after everything has been enqueued; call `wait()` (or synchronise the device) before reading host_out.
+
+    after_caller: order the three streams after the work already queued on the caller's current stream (needed when that work
+    touches the processor).  A caller that only streams batches through the runner passes False: consecutive `run` calls then
+    pipeline into each other (the copy-in of the next batch overlaps the tail of this one) -- the slots are handed over by events
+    that outlive a call, and the caller's stream is still ordered after the end of every batch.
 
     A result tensor stays referenced in its slot until the compute stream has been ordered after its copy-out, so that the
     caching allocator hands its memory out again in plain stream order (no record_stream bookkeeping, no allocator growth)."""
     assert len(host_frames) == len(host_out)
     caller = torch.cuda.current_stream(self.device)
-    for s in (self._s_in, self._s_compute, self._s_out):
-      s.wait_stream(caller)
+    if after_caller:
+      for s in (self._s_in, self._s_compute, self._s_out):
+        s.wait_stream(caller)
     for i, frame in enumerate(host_frames):
-      slot = i % self.slots
+      slot = (self._next + i) % self.slots
       with torch.cuda.stream(self._s_in):
-        if i >= self.slots:
-          self._s_in.wait_event(self._consumed[slot])  # the previous user of this slot has been processed
+        if self._used[slot]:
+          self._s_in.wait_event(self._consumed[slot])  # the previous user of this slot (this call's or an earlier one's) has been processed
         self._in[slot].copy_(frame, non_blocking=True)
         self._copied[slot].record(self._s_in)
       with torch.cuda.stream(self._s_compute):
@@ -53,12 +61,14 @@ class HostFrameRunner:
           self._results[slot] = None
         result = self.processor.process(self._in[slot], name)
         self._consumed[slot].record(self._s_compute)
+        self._used[slot] = True
         self._ready[slot].record(self._s_compute)
         self._results[slot] = result
       with torch.cuda.stream(self._s_out):
         self._s_out.wait_event(self._ready[slot])
         host_out[i].copy_(result, non_blocking=True)
         self._out_done[slot].record(self._s_out)
+    self._next = (self._next + len(host_frames)) % self.slots
     self._done.record(self._s_out)
     caller.wait_event(self._done)
 
