@@ -86,6 +86,21 @@ def test_wiener_shared_columns_geometry(impl, oracle, h, w, c):
   check('wiener', impl, oracle, {'sigmas': sigmas, 'tile_size': 32, 'overlap_factor': 4}, {'x': x})
 
 
+def test_wiener_shared_columns_repeatable():
+  """The CTAs hand spectra and accumulators over through shared memory between barriers: a missing one would show up as a
+  sporadic, large difference between runs (the only legitimate run-to-run variation is the order of the global float atomics)."""
+  import torch
+  import torch_darktable as td
+  h, w = 516, 1100
+  x = torch.from_numpy((synth.scene_rgb(h, w, 29)[..., :1] + np.random.default_rng(8).normal(0, 0.03, size=(h, w, 1))).astype(np.float32)).cuda()
+  wiener = td.Wiener(torch.device('cuda:0'), (w, h))
+  sig = torch.tensor([0.04], device='cuda')
+  first = wiener.process(x, sig).clone()
+  for _ in range(8):
+    again = wiener.process(x, sig)
+    assert float((again - first).abs().max()) < 2e-6
+
+
 @pytest.mark.parametrize('h,w', SIZES)
 def test_wiener_log_luminance(impl, oracle, h, w):
   rng = np.random.default_rng(6)
