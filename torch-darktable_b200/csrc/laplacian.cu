@@ -357,6 +357,103 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(const __grid_constan
   else a.out_fine[(int64_t)y * w + x] = f2h(val);
 }
 
+
+// The same assemble step for a 2 x 2 block of fine pixels per thread.  assemble_kernel executes about 600 instructions per pixel, most
+// of them integer work (ncu: ALU pipe 75 %, FMA 36 % at level 0): the boundary clamp, the parity tests inside expand_gaussian and the
+// 64-bit indices of its 27 two-byte loads, per pixel.  The four pixels (2 bx + {0,1}, 2 by + {0,1}) share the coarse centre (bx, by),
+// so one 3 x 3 coarse neighbourhood per plane serves all of them (9 loads instead of 9 + 6 + 6 + 4), their parities -- and with them
+// the tap sets and weights of expand_gaussian (laplacian.cu:111-140) -- are compile-time, and each pixel's sum still runs over its
+// taps in the reference's order (i outer, j inner), so the result is bit-identical.  The two gamma planes a pixel blends depend on
+// its own value; the block walks the planes any of its pixels needs (two when the four agree, as in smooth image regions).
+// Only for regions that no boundary clamp can reach (1 <= x <= w - 3): the host falls back to assemble_kernel otherwise.
+struct Taps9 {
+  float v[3][3];  // [j + 1][i + 1]: coarse (bx + i, by + j)
+};
+__device__ __forceinline__ Taps9 load_taps(const __half *__restrict__ coarse, int bx, int by, int cw) {
+  Taps9 t;
+  const __half *c = coarse + (int64_t)(by - 1) * cw + (bx - 1);
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) t.v[j][i] = h2f(c[j * cw + i]);
+  return t;
+}
+template <int XO, int YO>
+__device__ __forceinline__ float expand_from(const Taps9 &t) {  // expand_gaussian for the pixel with parities (XO, YO)
+  const float w[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  float c = 0.0f;
+#pragma unroll
+  for (int i = -1; i <= 1; i++)
+#pragma unroll
+    for (int j = -1; j <= 1; j++) {
+      if ((XO && i < 0) || (YO && j < 0)) continue;
+      const int wi = XO ? (2 * i + 1) : (2 * i + 2), wj = YO ? (2 * j + 1) : (2 * j + 2);
+      c += t.v[j + 1][i + 1] * w[wi] * w[wj];
+    }
+  return 4.0f * c;
+}
+struct Quad {
+  float p[4];  // (0,0), (1,0), (0,1), (1,1): index = XO + 2 * YO
+};
+__device__ __forceinline__ Quad expand_quad(const Taps9 &t) {
+  return Quad{{expand_from<0, 0>(t), expand_from<1, 0>(t), expand_from<0, 1>(t), expand_from<1, 1>(t)}};
+}
+
+template <bool kLevel0>
+__global__ void __launch_bounds__(kThreads) assemble2_kernel(const __grid_constant__ AssembleArgs a, CurveParams cp) {
+  const int bx = (a.rx0 >> 1) + blockIdx.x * 32 + (threadIdx.x & 31), by = (a.ry0 >> 1) + blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int x0 = 2 * bx, y0 = 2 * by;
+  if (x0 >= a.rx1 || y0 >= a.ry1) return;
+  const int w = a.fw;
+  const int cw = (w - 1) / 2 + 1;
+  // the four fine values, the gamma pair each of them blends and its weight (:238-250)
+  float v[4], tt[4];
+  int lo[4];
+  bool in[4];
+  int lo_min = G, lo_max = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = x0 + (k & 1), y = y0 + (k >> 1);
+    in[k] = x < a.rx1 && y < a.ry1;
+    v[k] = 0.0f;
+    if (in[k]) v[k] = kLevel0 ? h2f(f2h(__ldg(a.image + (int64_t)(y - a.max_supp) * a.width + (x - a.max_supp)))) : h2f(a.padded[(int64_t)y * w + x]);
+    int hi = 1;
+    for (; hi < G - 1 && ((float)hi + .5f) / (float)G <= v[k]; hi++);
+    lo[k] = hi - 1;
+    tt[k] = fminf(fmaxf(v[k] * G - ((float)lo[k] + .5f), 0.0f), 1.0f);
+    lo_min = min(lo_min, lo[k]), lo_max = max(lo_max, lo[k]);
+  }
+  const Quad base = expand_quad(load_taps(a.out_coarse, bx, by, cw));
+  float e0[4], e1[4];  // expand_gaussian of the planes lo and lo + 1 of each pixel
+#pragma unroll
+  for (int k = 0; k < 4; k++) e0[k] = 0.0f, e1[k] = 0.0f;
+  for (int g = lo_min; g <= lo_max + 1; g++) {
+    const Quad q = expand_quad(load_taps(a.proc_coarse[g], bx, by, cw));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (g == lo[k]) e0[k] = q.p[k];
+      if (g == lo[k] + 1) e1[k] = q.p[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (!in[k]) continue;
+    const int x = x0 + (k & 1), y = y0 + (k >> 1);
+    float f0, f1;
+    if (kLevel0) {
+      f0 = h2f(f2h(curve(v[k], (lo[k] + 0.5f) / (float)G, cp)));
+      f1 = h2f(f2h(curve(v[k], (lo[k] + 1.5f) / (float)G, cp)));
+    } else {
+      f0 = h2f(a.proc_fine[lo[k]][(int64_t)y * w + x]);
+      f1 = h2f(a.proc_fine[lo[k] + 1][(int64_t)y * w + x]);
+    }
+    const float l0 = f0 - e0[k], l1 = f1 - e1[k];
+    const float val = base.p[k] + (l0 * (1.0f - tt[k]) + l1 * tt[k]);
+    if (kLevel0) a.out_image[(int64_t)(y - a.max_supp) * a.width + (x - a.max_supp)] = h2f(f2h(val));
+    else a.out_fine[(int64_t)y * w + x] = f2h(val);
+  }
+}
+
 }  // namespace
 }  // namespace tdb
 
@@ -428,9 +525,19 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
     a.fw = p.w[l], a.fh = p.h[l];
     a.rx0 = rx0[l], a.ry0 = ry0[l], a.rx1 = rx1[l], a.ry1 = ry1[l];
     a.max_supp = p.max_supp, a.width = width;
-    const dim3 grid(div_up(a.rx1 - a.rx0, 32), div_up(a.ry1 - a.ry0, 8));
-    if (l == 0) assemble_kernel<true><<<grid, kThreads, 0, s>>>(a, cp);
-    else assemble_kernel<false><<<grid, kThreads, 0, s>>>(a, cp);
+    // 2 x 2 pixels per thread where no boundary clamp can act (clamp_boundary leaves 1 <= x <= w - 3 alone): the region is widened
+    // to even bounds (the extra pixels are valid results nobody reads)
+    const int ex0 = a.rx0 & ~1, ey0 = a.ry0 & ~1, ex1 = min(a.fw, (a.rx1 + 1) & ~1), ey1 = min(a.fh, (a.ry1 + 1) & ~1);
+    if (ex0 >= 2 && ey0 >= 2 && ex1 <= a.fw - 2 && ey1 <= a.fh - 2) {
+      if (l > 0) a.rx0 = ex0, a.ry0 = ey0, a.rx1 = ex1, a.ry1 = ey1;  // level 0 keeps the exact image rectangle (max_supp is even)
+      const dim3 grid2(div_up(a.rx1 - a.rx0, 64), div_up(a.ry1 - a.ry0, 16));
+      if (l == 0) assemble2_kernel<true><<<grid2, kThreads, 0, s>>>(a, cp);
+      else assemble2_kernel<false><<<grid2, kThreads, 0, s>>>(a, cp);
+    } else {
+      const dim3 grid(div_up(a.rx1 - a.rx0, 32), div_up(a.ry1 - a.ry0, 8));
+      if (l == 0) assemble_kernel<true><<<grid, kThreads, 0, s>>>(a, cp);
+      else assemble_kernel<false><<<grid, kThreads, 0, s>>>(a, cp);
+    }
     if (int e = check_launch("laplacian_assemble")) return e;
   }
   return TDB_OK;
