@@ -195,7 +195,7 @@ def test_laplacian(impl, oracle, sigma, shadows, highlights, clarity, h, w):
 
 def test_host_frame_runner_streams_batches():
   """HostFrameRunner: pinned host frames in, pinned host results out, three streams; consecutive batches queued without a host
-  wait in between (after_caller=False) hand their slots over by events.  Every result must equal ImageProcessor.process."""
+  wait in between (after_caller=False) hand their slots over by events.  Every result must equal ImageProcessor.process (up to the run-to-run noise of the float atomics)."""
   import torch
   import torch_darktable as td
   from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
@@ -212,5 +212,8 @@ def test_host_frame_runner_streams_batches():
   runner.run(frames[5:9], outs[5:9], after_caller=False)
   runner.run(frames[9:], outs[9:])
   runner.wait()
+  # two runs of the same frame are not bit-identical (the Wiener accumulator is filled with float atomics in arrival order): a frame
+  # that went through the wrong slot or an unfinished copy would differ everywhere, a legitimate one by 1 LSB on a few samples
   for i, (got, ref) in enumerate(zip(outs, want)):
-    assert torch.equal(got, ref), f'frame {i} differs'
+    d = (got.to(torch.int16) - ref.to(torch.int16)).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 1e-4, f'frame {i}: max {int(d.max())} LSB, {float((d > 0).float().mean()):.2e} differ'
