@@ -480,11 +480,10 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
   // level of the input's pyramid seeds the reconstruction (laplacian.cu:515-528)
   auto input_level = [&](int l) { return base + (l == L - 1 ? p.output[l] : p.padded[l]); };
   {
-    static bool attr = false;
+    static unsigned long long attr = 0;
     constexpr int bytes = NP * P1H * P1S * sizeof(float);
-    if (!attr) {
+    if (first_use_on_device(attr)) {
       cudaFuncSetAttribute(reduce1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      attr = true;
     }
     Reduce1Args r{};
     r.in = lum, r.width = width, r.height = height, r.max_supp = p.max_supp;

@@ -13,7 +13,17 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are siz
 
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
-int check_launch(const char *what);  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
+int check_launch(const char *what);
+// Kernel attributes (cudaFuncSetAttribute: dynamic shared memory above 48 KB) belong to a device's context: they are set on the
+// first launch per DEVICE, not per process, so that one process may drive several GPUs.  `seen` = a static bit mask at the call site.
+inline bool first_use_on_device(unsigned long long &seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
 void count_launches(int n);
 // a per-device side stream ordered after everything already queued on `main` (returns `main` itself when unavailable)
 cudaStream_t fork_side(cudaStream_t main);

@@ -16,6 +16,7 @@
 // No process-global device state: windows and sigmas travel as kernel arguments.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "bilateral.cuh"
 #include "fft32.cuh"
@@ -763,21 +764,27 @@ int run_tiles_shared(const float *in, float *acc, int width, int height, int cha
   a.steps_per_row = (a.n_tx + shr::TPS - 1) / shr::TPS;
   a.n_pairs = (n_ty + 1) / 2;
   a.total_steps = a.steps_per_row * a.n_pairs * channels;
-  make_window(32, a.win);
-  for (int i = 0; i < 32; i++) a.w2[i] = a.win[i] * a.win[i] * (1.0f / 32.0f);
-  for (int k = 0; k < 32; k++) {
-    double re = 0.0, im = 0.0;
-    for (int r = 0; r < 32; r++) {
-      const double ang = -2.0 * 3.14159265358979323846 * k * r / 32.0;
-      re += a.win[r] * cos(ang), im += a.win[r] * sin(ang);
+  // window, its squares / 32, its transform and the four-lane twiddles depend on nothing but K: built once per process
+  static const shr::Args tables = [] {
+    shr::Args t{};
+    make_window(32, t.win);
+    for (int i = 0; i < 32; i++) t.w2[i] = t.win[i] * t.win[i] * (1.0f / 32.0f);
+    for (int k = 0; k < 32; k++) {
+      double re = 0.0, im = 0.0;
+      for (int r = 0; r < 32; r++) {
+        const double ang = -2.0 * 3.14159265358979323846 * k * r / 32.0;
+        re += t.win[r] * cos(ang), im += t.win[r] * sin(ang);
+      }
+      t.what[k] = fft::cpx{(float)re, (float)im};
     }
-    a.what[k] = fft::cpx{(float)re, (float)im};
-  }
-  fft::make_quad_twiddles(a.tw);
-  static bool attr = false;
-  if (!attr) {
+    fft::make_quad_twiddles(t.tw);
+    return t;
+  }();
+  memcpy(a.win, tables.win, sizeof a.win), memcpy(a.w2, tables.w2, sizeof a.w2);
+  memcpy(a.what, tables.what, sizeof a.what), memcpy(a.tw, tables.tw, sizeof a.tw);
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(shr::wiener32_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
-    attr = true;
   }
   const int grid = a.total_steps < 2 * kNumSMs ? a.total_steps : 2 * kNumSMs;
   shr::wiener32_shared_kernel<<<grid, kThreads, shr::kSmemBytes, s>>>(a);
@@ -808,23 +815,21 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   const int64_t cap = (int64_t)kNumSMs * 8;  // persistent-style grid: a few CTAs per SM, each warp loops over tile pairs
   if (ctas > cap) ctas = cap;
   const size_t smem = (size_t)kWarps * sub * 2 * tile * (tile + 1) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
-    attr = true;
   }
   if (tile == 32 && a.stride == shr::ST && use_shared_columns()) return run_tiles_shared(in, acc, width, height, channels, sigmas, sigma_value, s);
   if (tile == 32) {
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
-    static bool attr32 = false;
-    if (!attr32) {
+    static unsigned long long attr32 = 0;
+    if (first_use_on_device(attr32)) {
       cudaFuncSetAttribute(wiener32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-      attr32 = true;
     }
     // interior pairs: oy = (gy - shift) * stride in [0, height - 32], ox0 = (2 px - shift) * stride >= 0, ox0 + stride + 32 <= width
     const int st = a.stride, shift = 32 / st;
