@@ -1,32 +1,32 @@
-"""JPEG output of the sRGB result (reference torch_darktable/jpeg.py:1-32): nvJPEG behind `extension.Jpeg`."""
+"""JPEG output of the uint8 sRGB result.
 
-from enum import IntEnum
+API of the reference's torch_darktable/jpeg.py (`Jpeg().encode(image, quality, input_format, subsampling, progressive)` -> 1-D uint8
+CPU tensor with the stream; `InputFormat`, `Subsampling`, `JpegException`); the coder behind it is libtdb200's nvJPEG binding
+(csrc/jpeg.cu): stream-ordered on torch's current stream, reading pitched images in place."""
 
-from .extension import extension
+import enum
 
-JpegException = extension.JpegException
+from .extension import extension as _ext
 
-
-class InputFormat(IntEnum):
-  BGR = extension.JpegInputFormat.BGR
-  RGB = extension.JpegInputFormat.RGB
-  BGRI = extension.JpegInputFormat.BGRI
-  RGBI = extension.JpegInputFormat.RGBI
-
-
-class Subsampling(IntEnum):
-  CSS_444 = extension.JpegSubsampling.CSS_444
-  CSS_422 = extension.JpegSubsampling.CSS_422
-  CSS_GRAY = extension.JpegSubsampling.CSS_GRAY
+JpegException = _ext.JpegException
+# the wrapper-level enums carry the values of the binding's (reference csrc/jpeg_encoder.h:6-17)
+InputFormat = enum.IntEnum('InputFormat', {member.name: int(member) for member in _ext.JpegInputFormat})
+Subsampling = enum.IntEnum('Subsampling', {member.name: int(member) for member in _ext.JpegSubsampling})
 
 
 class Jpeg:
+  """One nvJPEG handle + encoder state; not thread-safe, one object per stream of work."""
+
   def __init__(self):
-    self.jpeg = extension.Jpeg()
+    self.jpeg = _ext.Jpeg()
 
   def encode(self, image, quality=94, input_format=InputFormat.RGBI, subsampling=Subsampling.CSS_422, progressive=False):
-    """(H, W, 3) / (3, H, W) uint8 CUDA tensor -> 1-D uint8 CPU tensor holding the JPEG stream."""
+    """(H, W, 3) interleaved or (3, H, W) planar uint8 CUDA tensor -> JPEG stream (optimised Huffman tables, baseline unless
+    `progressive`)."""
     return self.jpeg.encode(image, quality, int(input_format), int(subsampling), progressive)
+
+  def __repr__(self):
+    return 'Jpeg'
 
 
 __all__ = ['InputFormat', 'Jpeg', 'JpegException', 'Subsampling']
