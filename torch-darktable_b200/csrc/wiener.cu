@@ -14,6 +14,11 @@
 //   The weight mask is separable and input-independent, so it is evaluated in closed form in the normalisation pass
 //   instead of being accumulated with atomics; the accumulator has no padding.
 // No process-global device state: windows and sigmas travel as kernel arguments.
+//
+// Three kernels share this file: wiener_tile_kernel (K = 16, the organisation above as first written), wiener32_kernel (K = 32, the
+// same organisation rebuilt around instruction count; used for overlap 2 and 8) and shr::wiener32_shared_kernel (K = 32, overlap 4 --
+// the default and the frame pipeline's configuration), which shares the column transforms between overlapping tiles and is
+// described where it is defined.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
