@@ -287,13 +287,13 @@ int bilateral_zero_grid(void *scratch, bil::GridDims g, cudaStream_t s) {
 }
 
 int bilateral_blur(void *scratch, bil::GridDims g, cudaStream_t s) {
-  static unsigned long long attr = 0;
+  static DeviceOnce attr;
   const size_t cells = (size_t)g.x * g.y * g.z;
   float *grid = static_cast<float *>(scratch), *blurred = grid + cells;
   const size_t bytes = (size_t)g.z * PYB * BX * sizeof(float);
-  if (first_use_on_device(attr)) {
+  attr.run([&] {
     cudaFuncSetAttribute(blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 51 * PYB * BX * 4);
-  }
+  });
   dim3 bgrid(div_up(g.x, BX), div_up(g.y, BY));
   blur_kernel<<<bgrid, kThreads, bytes, s>>>(grid, blurred, g);
   return check_launch("bilateral_blur");
@@ -307,12 +307,12 @@ int bilateral_build_grid(void *scratch, const float *lum, int width, int height,
   const bool gather = sigma_s >= 1.0f && (width - 1) / sigma_s <= (float)(g.x - 1) && (height - 1) / sigma_s <= (float)(g.y - 1) &&
                       (GPX + 1) * sigma_s + 8.0f <= (float)kMaxAxisPx;
   if (gather) {
-    static unsigned long long attr = 0;
-    if (first_use_on_device(attr)) {
+    static DeviceOnce attr;
+    attr.run([&] {
       cudaFuncSetAttribute(grid_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(grid_build_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
       cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
-    }
+    });
     float *blurred = static_cast<float *>(scratch) + (size_t)g.x * g.y * g.z;
     if (g.z <= 16 && sigma_s == 2.0f) {
       grid_build_kernel<16, true, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(

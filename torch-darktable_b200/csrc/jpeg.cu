@@ -215,6 +215,12 @@ int tdb_jpeg_retrieve(void *coder, uint8_t *host_out, size_t capacity, size_t *l
   TDB_REQUIRE(len <= capacity, "jpeg_retrieve: buffer of %zu bytes is too small for a %zu byte stream", capacity, len);
   if ((st = n.retrieve(c->handle, c->state, host_out, &len, as_stream(stream))) != NVJPEG_STATUS_SUCCESS)
     return fail("nvjpegEncodeRetrieveBitstream", st);
+  // the bytes must be in host_out when this returns, whatever nvJPEG does internally on a non-default stream
+  const cudaError_t err = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  if (err != cudaSuccess) {
+    set_error("jpeg_retrieve: %s", cudaGetErrorString(err));
+    return TDB_ECUDA;
+  }
   *length = len;
   c->pending = false;
   return TDB_OK;

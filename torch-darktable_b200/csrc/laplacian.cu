@@ -480,11 +480,11 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
   // level of the input's pyramid seeds the reconstruction (laplacian.cu:515-528)
   auto input_level = [&](int l) { return base + (l == L - 1 ? p.output[l] : p.padded[l]); };
   {
-    static unsigned long long attr = 0;
+    static DeviceOnce attr;
     constexpr int bytes = NP * P1H * P1S * sizeof(float);
-    if (first_use_on_device(attr)) {
+    attr.run([&] {
       cudaFuncSetAttribute(reduce1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    }
+    });
     Reduce1Args r{};
     r.in = lum, r.width = width, r.height = height, r.max_supp = p.max_supp;
     r.fw = p.w[0], r.fh = p.h[0], r.cw = p.w[1], r.ch = p.h[1];

@@ -447,13 +447,13 @@ size_t tdb_postprocess_scratch_bytes(int width, int height) {
 // `final_dst` receives the last pass; `stats` applies to the last launch.  Returns the number of CTAs of that launch in *nctas.
 static int run_smoothing(const float *in, float *final_dst, float *img_a, float *img_b, int width, int height, uint32_t filters, int passes,
                          const SmoothStats &stats, size_t *nctas, cudaStream_t s) {
-  static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) {
+  static DeviceOnce attr;
+  attr.run([&] {
     cudaFuncSetAttribute(smooth_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 1) * SPW * sizeof(float)));
     cudaFuncSetAttribute(smooth_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 2) * SPW * sizeof(float)));
     cudaFuncSetAttribute(smooth_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 3) * SPW * sizeof(float)));
     cudaFuncSetAttribute(smooth_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * (SH + 2 * 4) * SPW * sizeof(float)));
-  }
+  });
   const float *cur = in;
   int remaining = passes;
   while (remaining > 0) {

@@ -410,15 +410,15 @@ __global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, f
 }  // namespace
 
 int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, cudaStream_t s) {
-  static unsigned long long attr = 0;
+  static DeviceOnce attr;
   constexpr size_t bytes = SMEM_FLOATS * sizeof(float);
   constexpr size_t bytes3 = v3::SMEM_FLOATS * sizeof(float);
   static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
-  if (first_use_on_device(attr)) {
+  attr.run([&] {
     cudaFuncSetAttribute(rcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute(rcd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
     cudaFuncSetAttribute(rcd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
-  }
+  });
   // interior tiles (64 x 32) whose 88 x 56 patch lies inside the image; needs 16-byte aligned rows on both sides.  The tiling starts
   // at x = 32 so that the frame left to the 32 x 32 kernel is a ring of single tiles
   const int x_origin = T;

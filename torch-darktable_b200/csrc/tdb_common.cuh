@@ -5,6 +5,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/tdb200.h"
 
 namespace tdb {
@@ -13,17 +16,29 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are siz
 
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
-int check_launch(const char *what);
+int check_launch(const char *what);  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
 // Kernel attributes (cudaFuncSetAttribute: dynamic shared memory above 48 KB) belong to a device's context: they are set on the
-// first launch per DEVICE, not per process, so that one process may drive several GPUs.  `seen` = a static bit mask at the call site.
-inline bool first_use_on_device(unsigned long long &seen) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (seen & bit) return false;
-  seen |= bit;
-  return true;
-}  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter
+// first launch per DEVICE, not per process, so that one process may drive several GPUs -- and from several host threads (ctypes
+// releases the GIL; pipeline/tiled.py runs one thread per band).  The device's bit is published only AFTER the attributes have been
+// applied, under a mutex, so that no thread can launch a kernel whose opt-in is still pending.
+class DeviceOnce {
+ public:
+  template <class F>
+  void run(F &&apply) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_.load(std::memory_order_acquire) & bit) return;
+    std::lock_guard<std::mutex> lock(mutex_);
+    if (done_.load(std::memory_order_relaxed) & bit) return;
+    apply();
+    done_.fetch_or(bit, std::memory_order_release);
+  }
+
+ private:
+  std::atomic<unsigned long long> done_{0};
+  std::mutex mutex_;
+};
 void count_launches(int n);
 // a per-device side stream ordered after everything already queued on `main` (returns `main` itself when unavailable)
 cudaStream_t fork_side(cudaStream_t main);

@@ -787,10 +787,10 @@ int run_tiles_shared(const float *in, float *acc, int width, int height, int cha
   }();
   memcpy(a.win, tables.win, sizeof a.win), memcpy(a.w2, tables.w2, sizeof a.w2);
   memcpy(a.what, tables.what, sizeof a.what), memcpy(a.tw, tables.tw, sizeof a.tw);
-  static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) {
+  static DeviceOnce attr;
+  attr.run([&] {
     cudaFuncSetAttribute(shr::wiener32_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
-  }
+  });
   const int grid = a.total_steps < 2 * kNumSMs ? a.total_steps : 2 * kNumSMs;
   shr::wiener32_shared_kernel<<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   return check_launch("wiener_tiles");
@@ -811,8 +811,12 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   // scratch layout: [64 floats: job counters][accumulator][extra plane]; one memset clears counters and accumulator
   a.counters = reinterpret_cast<unsigned int *>(acc) - 64;
   if (!cleared) {
-    cudaMemsetAsync(a.counters, 0, ((size_t)width * height * channels + 64) * sizeof(float), s);
-    check_launch("wiener_zero_accumulator");
+    const cudaError_t cleared_err = cudaMemsetAsync(a.counters, 0, ((size_t)width * height * channels + 64) * sizeof(float), s);
+    if (cleared_err != cudaSuccess) {
+      set_error("wiener_zero_accumulator: %s", cudaGetErrorString(cleared_err));
+      return TDB_ECUDA;
+    }
+    if (int e = check_launch("wiener_zero_accumulator")) return e;
   }
   const int sub = 32 / tile;
   const int64_t warps_needed = (a.njobs + sub - 1) / sub;
@@ -820,22 +824,22 @@ int run_tiles(const float *in, float *acc, int width, int height, int channels, 
   const int64_t cap = (int64_t)kNumSMs * 8;  // persistent-style grid: a few CTAs per SM, each warp loops over tile pairs
   if (ctas > cap) ctas = cap;
   const size_t smem = (size_t)kWarps * sub * 2 * tile * (tile + 1) * sizeof(float);
-  static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) {
+  static DeviceOnce attr;
+  attr.run([&] {
     cudaFuncSetAttribute(wiener_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * 2 * 2 * 16 * 17 * 4);
-  }
+  });
   if (tile == 32 && a.stride == shr::ST && use_shared_columns()) return run_tiles_shared(in, acc, width, height, channels, sigmas, sigma_value, s);
   if (tile == 32) {
     const size_t smem32 = (size_t)kWarps * 32 * 33 * sizeof(float2);
-    static unsigned long long attr32 = 0;
-    if (first_use_on_device(attr32)) {
+    static DeviceOnce attr32;
+    attr32.run([&] {
       cudaFuncSetAttribute(wiener32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
       cudaFuncSetAttribute(wiener32_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-    }
+    });
     // interior pairs: oy = (gy - shift) * stride in [0, height - 32], ox0 = (2 px - shift) * stride >= 0, ox0 + stride + 32 <= width
     const int st = a.stride, shift = 32 / st;
     a.gy_lo = shift, a.gy_hi = (height - 32) / st + shift;

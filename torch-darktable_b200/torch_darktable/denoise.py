@@ -69,6 +69,10 @@ class Wiener:
 
   def process_log_luminance(self, image: torch.Tensor, noise: float | torch.Tensor, eps: float = 1e-4) -> torch.Tensor:
     if isinstance(noise, float):  # fused path: log-luminance, tiles and the Lab write-back without intermediate planes
+      # the reference fails in process() on the (H, W, 1) log-luminance plane (denoise.py:87-89): same exception, same text
+      got, expected = torch.Size((*image.shape[:2], 1)), (self._wiener.height, self._wiener.width, 1)
+      if image.dim() != 3 or tuple(got) != expected:
+        raise RuntimeError(f'Wiener input shape {got} != expected {expected}')
       return self._wiener.process_log_luminance(image, noise, eps)
     log_luminance = extension.compute_log_luminance(image, eps=eps)
     return extension.modify_log_luminance(image, self.process(log_luminance.unsqueeze(2), noise).squeeze(2), eps=eps)

@@ -665,6 +665,7 @@ class Wiener(_Workspace):
   def process_log_luminance(self, rgb: torch.Tensor, noise: float, eps: float = 1e-4) -> torch.Tensor:
     """compute_log_luminance -> process -> modify_log_luminance (denoise.py:54-58) without the intermediate planes."""
     _rgb_image(rgb)
+    self._check_size(rgb)
     h, w = rgb.size(0), rgb.size(1)
     out = torch.empty_like(rgb)
     scratch = self._ensure_scratch(lib.tdb_wiener_scratch_bytes(w, h, 1, self._tile))
