@@ -18,6 +18,7 @@ MP24 = (4000, 6000)   # configs[1]
 UHD = (2160, 3840)    # configs[2]
 MP50 = (6144, 8192)   # configs[3]
 MP20 = (3648, 5472)   # configs[4]
+MP200 = (12288, 16384)  # configs[4], the oversize frame
 
 
 @pytest.fixture(scope='module')
@@ -168,6 +169,31 @@ def test_pipeline_20mp_row_bands_equal_whole_frame(td):
   want = whole.process_image_set({'a': torch.from_numpy(frame).to(dev)})['a']
   rows = [[torch.from_numpy(r.copy()).to(dev) for r in split_rows(frame, w, h, 4, 32)]]
   got, _ = run_threads(4, lambda col: TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, WB, col), rows)
+  assert_u8_close(torch.from_numpy(np.ascontiguousarray(got[0])), want, 5e-4, beyond=1e-6)
+
+
+def test_pipeline_200mp_eight_row_bands_equal_whole_frame(td):
+  """The 16384 x 12288 frame of BASELINE.json configs[4] split into EIGHT row bands of 1536 rows (+ 96-row halos), on one GPU through a
+  thread collective (the NCCL form of the same code runs in tests/test_tiled.py when the box has several GPUs), against the untiled
+  ImageProcessor on the same 201 MP frame.  sigma_s = 8: at sigma_s = 2 the full frame's grid saturates in y and the split refuses
+  it (pipeline/tiled.py).  <= 5e-4 of the samples different, <= 1e-6 of them by more than 1 LSB (the stale-cell band of the
+  reference's RCD just inside its margin depends on absolute positions)."""
+  import torch
+  from test_tiled import WB, make_settings, run_threads
+  from torch_darktable.pipeline import ImageProcessor, ImageTransform
+  from torch_darktable.pipeline.tiled import TiledFrameProcessor, partition_rows
+  h, w = MP200
+  dev = torch.device('cuda:0')
+  packed, _ = device_packed(td, h, w, 201)
+  settings = make_settings('rcd', 'adaptive_aces', 1.0, bil_sigma_spatial=8.0, bil_sigma_luminance=0.1)
+  whole = ImageProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, WB, ImageTransform.none)
+  want = whole.process_image_set({'a': packed})['a']
+  del whole
+  torch.cuda.empty_cache()
+  rb = w * 3 // 2
+  rows = [[packed[y0 * rb: y1 * rb] for (y0, y1) in partition_rows(h, 8, 32)]]
+  got, proc = run_threads(8, lambda col: TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, WB, col), rows)
+  assert proc.band.y1 - proc.band.y0 == 1536
   assert_u8_close(torch.from_numpy(np.ascontiguousarray(got[0])), want, 5e-4, beyond=1e-6)
 
 

@@ -26,6 +26,7 @@ def main():
   ap.add_argument('--iters', type=int, default=10)
   ap.add_argument('--kernels', action='store_true', help='also print the per-kernel times of one call of every stage (ours only)')
   ap.add_argument('--quick', action='store_true', help='small shapes (smoke test of the script itself)')
+  ap.add_argument('--configs', default='2,4,1', help='comma-separated BASELINE.json config numbers to run (2 = 24 MP stages, 4 = 50 MP local contrast, 1 = 12 MP chain)')
   args = ap.parse_args()
   sys.path.insert(0, str(ROOT / ('torch-darktable_b200' if args.impl == 'ours' else 'baseline/_ref')))
   import torch
@@ -80,6 +81,16 @@ def main():
 
   pat = td.BayerPattern.RGGB
   wb = torch.tensor([1.8, 1.0, 2.1], device=dev)
+  wanted = set(args.configs.split(','))
+  if '2' in wanted:
+    config2(args, td, torch, dev, gen, ours, rotate, run, pat, wb)
+  if '4' in wanted:
+    config4(args, td, torch, dev, gen, ours, rotate, run)
+  if '1' in wanted:
+    config1(args, td, torch, dev, gen, ours, rotate, run, pat, wb)
+
+
+def config2(args, td, torch, dev, gen, ours, rotate, run, pat, wb):
 
   # ---- config 2 (24 MP packed -> unpack + demosaic) and the pointwise stages at the same shape -------------------------------
   w, h = (1536, 1024) if args.quick else (6000, 4000)
@@ -131,17 +142,19 @@ def main():
   del wiener, rgb, lum
   torch.cuda.empty_cache()
 
+
+def config4(args, td, torch, dev, gen, ours, rotate, run):
   # ---- config 4 (50 MP local contrast) ---------------------------------------------------------------------------------------
   w, h = (2048, 1536) if args.quick else (8192, 6144)
   c = 'config4 50MP'
   lum = rotate(lambda: torch.rand((h, w), device=dev, generator=gen), w * h * 4)
-  for ss in (8.0, 4.0):
-    bil = td.Bilateral(dev, (w, h), sigma_s=ss, sigma_r=0.2)
+  for ss, sr in ((8.0, 0.1), (8.0, 0.2), (4.0, 0.2), (2.0, 0.2)):  # 2 / 0.2 at 8192 px: the reference's saturating grid (3001 x 2251 x 6)
+    bil = td.Bilateral(dev, (w, h), sigma_s=ss, sigma_r=sr)
     cells = 1
     for d in bil._bilateral.grid_size() if ours else ():
       cells *= d
     grid_bpp = 4.0 * cells / (w * h)
-    run(c, f'Bilateral luminance (sigma_s {ss:g}, sigma_r 0.2)', w, h, round(12.0 + 2 * grid_bpp, 3) if ours else 12.0,
+    run(c, f'Bilateral luminance (sigma_s {ss:g}, sigma_r {sr:g})', w, h, round(12.0 + 2 * grid_bpp, 3) if ours else 12.0,
         lambda x, bil=bil: bil.process(x, 0.4), lum, f'grid {grid_bpp:.2f} B/px each way' if ours else '')
     del bil
   rgb = rotate(lambda: torch.rand((h, w, 3), device=dev, generator=gen), w * h * 12)
@@ -155,6 +168,8 @@ def main():
   del lap, lum
   torch.cuda.empty_cache()
 
+
+def config1(args, td, torch, dev, gen, ours, rotate, run, pat, wb):
   # ---- config 1 (12 MP, the chain the reference would run through its torch path) -------------------------------------------------
   w, h = (1024, 768) if args.quick else (4096, 3000)
   c = 'config1 12MP'

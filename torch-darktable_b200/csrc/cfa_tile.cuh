@@ -33,9 +33,9 @@ __device__ __forceinline__ void resolve_gains(CfaSource &s, uint32_t filters) {
 }
 
 __device__ __forceinline__ float finish_sample(const CfaSource &s, uint32_t raw, int y, int x) {
-  float v = (float)raw * (1.0f / 4095.0f);
+  float v = __fmul_rn((float)raw, 1.0f / 4095.0f);  // no FMA contraction with the black level: fused = decode12_float(x) - black
   if (s.apply) {
-    v -= s.black;
+    v = __fsub_rn(v, s.black);
     // selects on compile-time indices: a dynamically indexed member would push the whole struct into local memory
     if (s.apply == 2) v = clip01(v * ((y & 1) ? ((x & 1) ? s.gain[1][1] : s.gain[1][0]) : ((x & 1) ? s.gain[0][1] : s.gain[0][0])));
   }

@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kThreads) decode12_f32_kernel(const uint8_t *_
       int y = (int)(i0 / width), x = (int)(i0 - (int64_t)y * width);
 #pragma unroll
       for (int k = 0; k < 16; k += 2) {
-        float v0 = (float)px[k] * scale - wb.black, v1 = (float)px[k + 1] * scale - wb.black;
+        // two roundings, not one FMA: the fused result must equal decode12_float(x) - black of the stage-by-stage path bit for bit
+        float v0 = __fsub_rn(__fmul_rn((float)px[k], scale), wb.black), v1 = __fsub_rn(__fmul_rn((float)px[k + 1], scale), wb.black);
         if (wb.apply == 2) {
           v0 = clip01(v0 * wb.g[y & 1][0]);  // x is even for the first sample of a pair (width is even)
           v1 = clip01(v1 * wb.g[y & 1][1]);
@@ -106,10 +107,10 @@ __global__ void __launch_bounds__(kThreads) decode12_f32_kernel(const uint8_t *_
     const uint8_t *b = in + p * 3;
     uint32_t p0, p1;
     unpack_pair<kIds>((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16), p0, p1);
-    float v0 = (float)p0 * scale, v1 = (float)p1 * scale;
+    float v0 = __fmul_rn((float)p0, scale), v1 = __fmul_rn((float)p1, scale);
     if (kFused && wb.apply) {
       const int y = (int)((2 * p) / width);
-      v0 -= wb.black, v1 -= wb.black;
+      v0 = __fsub_rn(v0, wb.black), v1 = __fsub_rn(v1, wb.black);
       if (wb.apply == 2) v0 = clip01(v0 * wb.g[y & 1][0]), v1 = clip01(v1 * wb.g[y & 1][1]);
     }
     out[2 * p] = v0, out[2 * p + 1] = v1;
