@@ -280,6 +280,13 @@ int tdb_jpeg_encode(void *coder, const uint8_t *image, int width, int height, in
                     int input_format, int quality, int subsampling, int progressive, size_t *length, tdb_stream_t stream);
 int tdb_jpeg_retrieve(void *coder, uint8_t *host_out, size_t capacity, size_t *length, tdb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Pipe-throughput probes (csrc/probe.cu): kernels that keep ONLY the FP32 FMA pipe / ONLY the MUFU unit busy, for the
+ * denominators of the non-HBM rooflines in bench.py (SURVEY.md 8d asks for FLOP/s beside B/px for the Wiener tiles;
+ * the reference has no counterpart).  The caller times the launch with CUDA events; *flops / *ops = the work it does. */
+int tdb_probe_fp32(float *sink, int iters, double *flops, tdb_stream_t stream);
+int tdb_probe_mufu(float *sink, int iters, double *ops, tdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

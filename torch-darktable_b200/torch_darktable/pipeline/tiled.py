@@ -9,6 +9,7 @@ single-GPU pipeline has its global barriers:
   green sums (2 floats, SUM)   -> global green-equilibration ratio          (postprocess.cu:355-366)
   bounds     (2 floats, MIN/MAX) -> normalisation, with the EMA of ImageProcessor (image_processor.py:288-290)
   metrics    (6 floats, SUM)   -> tone-mapping metrics, with their EMA      (image_processor.py:292-294)
+(the fused path carries the first two in ONE all-gather of six floats per rank: two latency-bound collectives per frame)
 
 Band boundaries are multiples of 8 rows, which keeps the Bayer phase, the Wiener tile phase (stride 8), the sampling phase of
 the bounds / metrics (stride 8) and -- for sigma_s in {1, 2, 4, 8} -- the bilateral grid phase identical to the untiled frame, so
@@ -97,22 +98,30 @@ class DistCollective:
     self.rank = dist.get_rank(group)
     self.world = dist.get_world_size(group)
 
-  def exchange_halos(self, own: torch.Tensor, row_bytes: int, band: Band) -> torch.Tensor:
-    """own: this rank's packed rows (uint8, (y1 - y0) * row_bytes).  Returns the padded band (halo above, own, halo below)."""
+  def exchange_halos(self, padded: torch.Tensor, row_bytes: int, band: Band) -> torch.Tensor:
+    """padded: the rank's persistent band buffer (halo above | own rows | halo below, uint8) whose middle part already holds the own
+    rows.  The first / last `halo` own rows go to the neighbours and theirs arrive straight in the halo parts: one batched
+    isend / irecv, no staging copies (slices of a 1-D tensor are contiguous), no concatenation."""
     dist = self.dist
-    top = torch.empty(band.top * row_bytes, dtype=torch.uint8, device=own.device)
-    bottom = torch.empty(band.bottom * row_bytes, dtype=torch.uint8, device=own.device)
+    t, b, n = band.top * row_bytes, band.bottom * row_bytes, padded.numel()
     ops = []
     if band.top:      # my first rows go up, the upper neighbour's last rows come down
-      ops.append(dist.P2POp(dist.isend, own[: band.top * row_bytes].contiguous(), self.rank - 1, self.group))
-      ops.append(dist.P2POp(dist.irecv, top, self.rank - 1, self.group))
+      ops.append(dist.P2POp(dist.isend, padded[t: 2 * t], self.rank - 1, self.group))
+      ops.append(dist.P2POp(dist.irecv, padded[:t], self.rank - 1, self.group))
     if band.bottom:
-      ops.append(dist.P2POp(dist.isend, own[own.numel() - band.bottom * row_bytes:].contiguous(), self.rank + 1, self.group))
-      ops.append(dist.P2POp(dist.irecv, bottom, self.rank + 1, self.group))
+      ops.append(dist.P2POp(dist.isend, padded[n - 2 * b: n - b], self.rank + 1, self.group))
+      ops.append(dist.P2POp(dist.irecv, padded[n - b:], self.rank + 1, self.group))
     if ops:
       for req in dist.batch_isend_irecv(ops):
         req.wait()
-    return torch.cat([top, own, bottom])
+    return padded
+
+  def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+    """(world, n) stack of every rank's vector: ONE collective carries the green sums, the minima and the maxima of a band; each
+    rank then reduces the rows itself, in rank order (bit-identical on every rank)."""
+    out = torch.empty((self.world, t.numel()), dtype=t.dtype, device=t.device)
+    self.dist.all_gather_into_tensor(out, t.contiguous().reshape(1, -1), group=self.group)
+    return out
 
   def all_reduce(self, t: torch.Tensor, op: str) -> torch.Tensor:
     dist = self.dist
@@ -144,11 +153,22 @@ class ThreadCollective:
     hub.barrier.wait()  # nobody overwrites a slot before everybody has read it
     return values
 
-  def exchange_halos(self, own: torch.Tensor, row_bytes: int, band: Band) -> torch.Tensor:
-    rows = self._gather(own)
-    top = rows[self.rank - 1][rows[self.rank - 1].numel() - band.top * row_bytes:] if band.top else own[:0]
-    bottom = rows[self.rank + 1][: band.bottom * row_bytes] if band.bottom else own[:0]
-    return torch.cat([top, own, bottom])
+  def exchange_halos(self, padded: torch.Tensor, row_bytes: int, band: Band) -> torch.Tensor:
+    bufs = self._gather((padded, band))
+    t, b = band.top * row_bytes, band.bottom * row_bytes
+    if band.top:     # the upper neighbour's last own rows
+      up, ub = bufs[self.rank - 1]
+      end = up.numel() - ub.bottom * row_bytes
+      padded[:t].copy_(up[end - t: end])
+    if band.bottom:  # the lower neighbour's first own rows
+      dn, db = bufs[self.rank + 1]
+      start = db.top * row_bytes
+      padded[padded.numel() - b:].copy_(dn[start: start + b])
+    self.hub.barrier.wait()  # nobody refills its buffer before the neighbours have read it
+    return padded
+
+  def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+    return torch.stack(self._gather(t))
 
   def all_reduce(self, t: torch.Tensor, op: str) -> torch.Tensor:
     stacked = torch.stack(self._gather(t))
@@ -230,6 +250,22 @@ class TiledFrameProcessor:
   def owned_rows(self) -> tuple[int, int]:
     return self.band.y0, self.band.y1
 
+  def own_rows_buffer(self) -> torch.Tensor:
+    """The part of the persistent padded band buffer that holds this rank's own packed rows.  A producer that writes the rows
+    straight into it (a raw-file reader, an H2D copy) and then passes this very tensor to `process` saves the band-sized copy."""
+    b = self.band
+    if getattr(self, '_padded', None) is None:
+      p0, p1 = b.padded
+      self._padded = torch.empty((p1 - p0) * self.row_bytes, dtype=torch.uint8, device=self.device)
+    t = b.top * self.row_bytes
+    return self._padded[t: t + (b.y1 - b.y0) * self.row_bytes]
+
+  def _fill_padded(self, own_packed_rows: torch.Tensor) -> torch.Tensor:
+    view = self.own_rows_buffer()
+    if own_packed_rows.data_ptr() != view.data_ptr():
+      view.copy_(own_packed_rows)
+    return self._padded
+
   def _own(self, image: torch.Tensor) -> torch.Tensor:
     """Rows this rank owns, out of a tensor laid out over the padded band."""
     return image[self.band.top: self.band.top + (self.band.y1 - self.band.y0)]
@@ -248,7 +284,8 @@ class TiledFrameProcessor:
     return self._frame, self._post, self._wiener, self._bil
 
   def _process_fused(self, packed: torch.Tensor, size) -> torch.Tensor:
-    """The band through the fused frame kernels; three all-gathers of six floats where the single-GPU pipeline has its barriers."""
+    """The band through the fused frame kernels; TWO collectives of six floats per frame -- an all-gather of the smoothing statistics
+    (green sums, minima, maxima) and an all-reduce of the metric sums -- where the single-GPU pipeline has its barriers."""
     from ..extension import extension
     b, s, col = self.band, self.settings, self.collective
     frame, post, wiener, bil = self._fused_objects(size)
@@ -256,8 +293,9 @@ class TiledFrameProcessor:
     rgb = self.td.demosaic_packed(packed, size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
                                   white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
     smoothed, raw = frame.smooth_band(post, rgb, lo, hi)
-    sums = col.all_reduce(raw[0:2], 'sum')
-    mins, maxs = col.all_reduce(raw[[2, 4]], 'min'), col.all_reduce(raw[[3, 5]], 'max')
+    stats = col.all_gather(raw)  # (world, 6): one collective for the green sums, the minima and the maxima
+    sums = stats[:, 0:2].sum(0)
+    mins, maxs = stats[:, [2, 4]].min(0).values, stats[:, [3, 5]].max(0).values
     one = torch.ones_like(sums[0])
     ratio = torch.where((sums[0] > 0) & (sums[1] > 0), sums[1] / sums[0], one).reshape(1)
     # bounds of the equilibrated image: the G1 greens take the ratio (x -> max(0, x * ratio) is monotone), csrc/postprocess.cu
@@ -291,7 +329,7 @@ class TiledFrameProcessor:
     b, s, ops, col = self.band, self.settings, self.ops, self.collective
     if own_packed_rows.numel() != (b.y1 - b.y0) * self.row_bytes:
       raise ValueError(f'expected {(b.y1 - b.y0) * self.row_bytes} packed bytes for rows {b.y0}..{b.y1}, got {own_packed_rows.numel()}')
-    packed = col.exchange_halos(own_packed_rows, self.row_bytes, b)
+    packed = col.exchange_halos(self._fill_padded(own_packed_rows), self.row_bytes, b)
     p0, p1 = b.padded
     size = (self.width, p1 - p0)
     if self.fused:
