@@ -230,8 +230,8 @@ def stage_table(table: dict, peak_gbs: float, pipe: dict, sm_mhz: float | None, 
       pcts = {'hbm': k.get('dram_pct'), 'fp32': k.get('fma_pipe_pct'), 'mufu': k.get('xu_pipe_pct'), 'issue': k.get('issue_pct')}
       pipes = {b: p for b, p in pcts.items() if p is not None and b != 'issue'}
       bound = max(pipes, key=pipes.get) if pipes else 'issue'
-      if pcts['issue'] is not None and pipes and pcts['issue'] > max(pipes.values()) and max(pipes.values()) < 60.0:
-        bound = 'issue'  # no single pipe is near its limit: the schedulers' issue slots (latency / dependency stalls) are the limit
+      if pcts['issue'] is not None and pipes and pcts['issue'] > max(pipes.values()) and max(pipes.values()) < 40.0:
+        bound = 'issue'  # no pipe is even 40 % busy: the kernel is limited by what the schedulers manage to issue (latency, dependencies)
       row['bound'], row['bound_pct_ncu'] = bound, pcts.get(bound)
       row['ncu_pcts'] = pcts
       sec = ms / 1e3
