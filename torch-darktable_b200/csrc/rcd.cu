@@ -12,13 +12,18 @@
 // positions (or zero).  `stale_cell` reproduces exactly that for a FRESH reference workspace, so the output matches a
 // freshly constructed reference RCD object everywhere, including the band just inside the 7-px margin.  What the
 // reference leaks from the PREVIOUS frame (rows 2-3 of VH_dir) is deliberately not reproduced.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
 #include "cfa_tile.cuh"
 #include "rcd_planar.cuh"
+#include "rcd_strip.cuh"
 
 namespace tdb {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads256 = 256;
 constexpr int T = 32;          // output tile edge
 constexpr int HALO = 10;
 constexpr int P = T + 2 * HALO;  // patch edge (52)
@@ -60,7 +65,9 @@ struct TileRects {
   int start[5];          // prefix sums of the tile counts
 };
 
-// one 32 x 32 tile; `tile` = blockIdx.x of a 1-D launch over `rects`, (bx, by) = tile coordinates of a plain 2-D launch
+// one 32 x 32 tile; `tile` = blockIdx.x of a 1-D launch over `rects`, (bx, by) = tile coordinates of a plain 2-D launch.
+// kThreads = threads of the CTA that runs it (256 on its own and inside the tile kernel, 160 inside the strip kernel)
+template <int kThreads>
 __device__ __forceinline__ void rcd_tile(float *sm, const CfaSource &src_in, float *__restrict__ rgb, int width, int height, uint32_t filters,
                                          const TileRects &rects, int tile, int bx, int by) {
   CfaSource src = src_in;
@@ -386,10 +393,10 @@ __device__ __forceinline__ void rcd_tile(float *sm, const CfaSource &src_in, flo
   store_rgb_tile(outt, T * 3, rgb, x0, y0, T, T, width, height);
 }
 
-__global__ void __launch_bounds__(kThreads) rcd_kernel(CfaSource src, float *__restrict__ rgb, int width, int height, uint32_t filters,
+__global__ void __launch_bounds__(kThreads256) rcd_kernel(CfaSource src, float *__restrict__ rgb, int width, int height, uint32_t filters,
                                                        TileRects rects) {
   extern __shared__ __align__(16) float sm[];
-  rcd_tile(sm, src, rgb, width, height, filters, rects, blockIdx.x, blockIdx.x, blockIdx.y);
+  rcd_tile<kThreads256>(sm, src, rgb, width, height, filters, rects, blockIdx.x, blockIdx.x, blockIdx.y);
 }
 
 
@@ -405,7 +412,41 @@ __global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, f
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   if (b < n_interior) v3::rcd3_tile<kG0>(sm, src, rgb, width, height, filters, x_origin, by_lo, b % nbx, b / nbx);
-  else rcd_tile(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
+  else rcd_tile<kThreads256>(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
+}
+
+// ======================================================================================================================
+// Interior as column strips: rcd_strip.cuh.  A strip job = (strip, segment of its rows); the 32 x 32 frame tiles ride in the same
+// grid (its tail by default), run by the same 160-thread CTAs.
+template <bool kG0>
+__global__ void __launch_bounds__(v4::NT, 3) rcd_strip_kernel(const __grid_constant__ CUtensorMap tmap, const v4::StripArgs a, const TileRects rects) {
+  extern __shared__ __align__(128) float sm[];
+  int b = blockIdx.x;
+  const bool frame = a.frame_first ? b < a.n_frame : b >= a.n_strip_jobs;
+  if (frame) {
+    rcd_tile<v4::NT>(sm, a.src, a.rgb, a.width, a.height, a.filters, rects, a.frame_first ? b : b - a.n_strip_jobs, 0, 0);
+    return;
+  }
+  if (a.frame_first) b -= a.n_frame;
+  v4::rcd_strip<kG0>(sm, &tmap, a, b);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: libtdb200 does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static const EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int env_int(const char *name, int fallback) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : fallback;
 }
 }  // namespace
 
@@ -413,7 +454,7 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
   static DeviceOnce attr;
   constexpr size_t bytes = SMEM_FLOATS * sizeof(float);
   constexpr size_t bytes3 = v3::SMEM_FLOATS * sizeof(float);
-  static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads, "the frame tiles run inside the interior kernel's CTAs");
+  static_assert(v3::SMEM_FLOATS >= SMEM_FLOATS && v3::kThreads3 == kThreads256, "the frame tiles run inside the interior kernel's CTAs");
   attr.run([&] {
     cudaFuncSetAttribute(rcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     cudaFuncSetAttribute(rcd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes3);
@@ -429,6 +470,76 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
                                 : (reinterpret_cast<uintptr_t>(src.packed) % 4 == 0 && ((int64_t)width * height * 3 / 2) % 4 == 0));
   TileRects rects{};
   const int ntx = div_up(width, T), nty = div_up(height, T);
+
+  // ---- strips (rcd_strip.cuh): rows [32, y_end) of the columns [32, 32 + 64 nbx), y_end a multiple of 32 with 16 rows to spare below
+  // (the staging reads 13 rows ahead of the output, and a packed row copy may be rounded up to the next 16-byte boundary)
+  static const int use_strips = env_int("TDB_RCD_STRIPS", 1);
+  const int y_end = (height - 16) / 32 * 32;
+  const bool strip_align = src.cfa ? true : reinterpret_cast<uintptr_t>(src.packed) % 16 == 0;
+  if (use_strips && aligned && strip_align && nbx >= 1 && y_end >= 64 && (!src.cfa || encode_tiled())) {
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (src.cfa) {
+      const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height}, strides[1] = {(cuuint64_t)width * sizeof(float)};
+      const cuuint32_t box[2] = {(cuuint32_t)v4::PW, (cuuint32_t)v4::R}, estr[2] = {1, 1};
+      const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(src.cfa), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("RCD: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return TDB_ECUDA;
+      }
+    }
+    v4::StripArgs a{};
+    a.src = src, a.rgb = rgb, a.width = width, a.height = height, a.filters = filters, a.x_origin = x_origin;
+    a.nstrips = nbx, a.y_start = 32, a.n_iter = (y_end - 32) / v4::R;
+    // frame tiles: top, bottom, left, right of the strip area
+    const int ix0 = x_origin / T, ix1 = (x_origin + nbx * v4::TW) / T, iy0 = 1, iy1 = y_end / T;
+    const int rx0[4] = {0, 0, 0, ix1}, ry0[4] = {0, iy1, iy0, iy0};
+    const int rnx[4] = {ntx, ntx, ix0, ntx - ix1}, rny[4] = {iy0, nty - iy1, iy1 - iy0, iy1 - iy0};
+    int n = 0, total = 0;
+    for (int k = 0; k < 4; k++) {
+      if (rnx[k] <= 0 || rny[k] <= 0) continue;
+      rects.tx0[n] = rx0[k], rects.ty0[n] = ry0[k], rects.ntx[n] = rnx[k], rects.start[n] = total;
+      total += rnx[k] * rny[k], n++;
+    }
+    for (int k = n; k < 5; k++) rects.start[k] = total;
+    for (int k = n; k < 4; k++) rects.ntx[k] = 1;
+    rects.n = n;
+    a.n_frame = total;
+    // segments per strip: every segment pays ~1.1 iterations of pipeline fill; 3 CTAs x 148 SMs run at a time; the frame tiles (about
+    // 2.2 iterations of work each) fill the slots the strips leave free and whatever remains of them runs after the last wave
+    static const int forced = env_int("TDB_RCD_SEGMENTS", 0);
+    int best = 1;
+    double best_cost = 1e30;
+    const double slots = 3.0 * kNumSMs, frame_work = 2.2 * total;
+    for (int sgm = 1; sgm <= 64 && sgm <= a.n_iter; sgm++) {
+      const double jobs = (double)nbx * sgm, len = (double)a.n_iter / sgm + 1.1;
+      const double waves = ceil(jobs / slots);
+      const double free_work = (waves * slots - jobs) * len;
+      const double cost = waves * len + (frame_work > free_work ? 2.2 + (frame_work - free_work) / slots : 0.0);
+      if (cost < best_cost) best_cost = cost, best = sgm;
+    }
+    a.nseg = forced > 0 ? (forced < a.n_iter ? forced : a.n_iter) : best;
+    a.n_strip_jobs = a.nstrips * a.nseg;
+    static const int frame_first = env_int("TDB_RCD_FRAME_FIRST", 0);
+    a.frame_first = frame_first;
+    constexpr size_t bytes4 = v4::SMEM_FLOATS * sizeof(float);
+    static_assert(v4::SMEM_FLOATS >= SMEM_FLOATS, "the frame tiles run inside the strip kernel's CTAs");
+    static DeviceOnce attr4;
+    attr4.run([&] {
+      cudaFuncSetAttribute(rcd_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes4);
+      cudaFuncSetAttribute(rcd_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes4);
+      // three CTAs of 74.6 KB (+ 1 KB each for the system) need 227 of the SM's 228 KB as shared memory
+      cudaFuncSetAttribute(rcd_strip_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(rcd_strip_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
+    const int grid4 = a.n_strip_jobs + a.n_frame;
+    if (fc(0, 0, filters) == 1) rcd_strip_kernel<true><<<grid4, v4::NT, bytes4, s>>>(tmap, a, rects);
+    else rcd_strip_kernel<false><<<grid4, v4::NT, bytes4, s>>>(tmap, a, rects);
+    return check_launch("rcd_demosaic");
+  }
+
   if (aligned && width >= x_origin + v3::TW + v3::HX && nbx >= 1 && by_hi >= by_lo) {
     // the frame of 32 x 32 tiles around the interior: top, bottom, left, right
     const int ix0 = x_origin / T, ix1 = (x_origin + nbx * v3::TW) / T, iy0 = by_lo * v3::TH / T, iy1 = (by_hi + 1) * v3::TH / T;
@@ -446,13 +557,13 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
     const int n_interior = nbx * (by_hi - by_lo + 1);
     const int grid2 = n_interior + total;
     if (fc(0, 0, filters) == 1)
-      rcd3_kernel<true><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      rcd3_kernel<true><<<grid2, kThreads256, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
     else
-      rcd3_kernel<false><<<grid2, kThreads, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
+      rcd3_kernel<false><<<grid2, kThreads256, bytes3, s>>>(src, rgb, width, height, filters, x_origin, by_lo, nbx, n_interior, rects);
     return check_launch("rcd_demosaic");
   }
   dim3 grid(ntx, nty);
-  rcd_kernel<<<grid, kThreads, bytes, s>>>(src, rgb, width, height, filters, rects);
+  rcd_kernel<<<grid, kThreads256, bytes, s>>>(src, rgb, width, height, filters, rects);
   return check_launch("rcd_demosaic");
 }
 
