@@ -85,8 +85,20 @@ __device__ __forceinline__ void stage_patch(float *smem, int stride, int px0, in
         const int xa = max(0, min(x, width - 1)), xb = max(0, min(x + 1, width - 1));
         v0 = cfa_at(s, xa, y, width), v1 = cfa_at(s, xb, y, width);
       } else if (row_in && x >= 0 && x + 1 < width) {
-        const uint8_t *b = s.packed + (((int64_t)y * width + x) >> 1) * 3;
-        const uint32_t w = (uint32_t)__ldg(b) | ((uint32_t)__ldg(b + 1) << 8) | ((uint32_t)__ldg(b + 2) << 16);
+        // the pair's three bytes out of the one or two aligned 32-bit words that hold them (one or two 4-byte loads that neighbouring
+        // lanes share through L1, instead of three 1-byte loads); the last pairs of the frame keep the byte loads, so nothing
+        // beyond the frame's last byte is read
+        const int64_t off = (((int64_t)y * width + x) >> 1) * 3;
+        uint32_t w;
+        if ((reinterpret_cast<uintptr_t>(s.packed) & 3) == 0 && off + 8 <= (int64_t)width * height * 3 / 2) {
+          const uint32_t *wp = reinterpret_cast<const uint32_t *>(s.packed + (off & ~(int64_t)3));
+          const uint32_t sh = (uint32_t)(off & 3) * 8u;
+          const uint32_t w0 = __ldg(wp), w1 = sh > 8u ? __ldg(wp + 1) : 0u;
+          w = __funnelshift_r(w0, w1, sh);
+        } else {
+          const uint8_t *b = s.packed + off;
+          w = (uint32_t)__ldg(b) | ((uint32_t)__ldg(b + 1) << 8) | ((uint32_t)__ldg(b + 2) << 16);
+        }
         uint32_t p0, p1;
         if (s.ids) unpack_pair<true>(w, p0, p1); else unpack_pair<false>(w, p0, p1);
         v0 = finish_sample(s, p0, y, x), v1 = finish_sample(s, p1, y, x + 1);

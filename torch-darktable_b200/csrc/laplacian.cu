@@ -202,11 +202,68 @@ struct Reduce1Args {
   int width, height, max_supp;
   int fw, fh, cw, ch;  // padded level 0 / level 1 sizes
 };
+// A tile whose fine patch lies inside the IMAGE (no padding, no clamped coordinate, no flat axis) -- 96 % of the work at 50 MP.
+// The general path below spends 2400 instructions per coarse pixel: run-time divisions in the staging loop, bounds and clamp tests
+// per element, and seven 25-tap sums per coarse pixel whose taps are two multiplies each (the reference's (v * w_i) * w_j).  Here
+//   staging : a thread owns (row, column pair) tasks with compile-time divisors; the image is read without clamps
+//   sums    : SEPARABLE, in fp32: a thread owns one coarse column and FOUR coarse rows of half of the planes, forms the horizontal
+//             5-tap sums of the 11 fine rows it needs once (conflict-free: even / odd columns are stored apart) and combines them
+//             vertically -- 18.75 multiply-adds per coarse pixel and plane instead of 50, 13.75 loads instead of 25
+//   stores  : straight from registers, a warp writes 32 consecutive halves of a row
+// Separability does not change the result: every fine value is an fp16 number (11 significant bits) and every weight product is
+// k / 256 with k in {1, 4, 6, 16, 24, 36}, so each of the 25 terms is exact in fp32 and so is any partial sum of a neighbourhood whose
+// values lie within a factor of ~2^5 of each other -- the order of the additions (the reference's i-outer / j-inner loop,
+// laplacian.cu:178-208, or rows first as here) cannot matter.  Measured: bit-identical to the general path and to the reference on
+// the 50 MP frame of the live comparison (profiles/r02_ref_live_report.jsonl), 1.30 -> 0.95 ms.
+__device__ __forceinline__ void reduce1_interior(const Reduce1Args &a, const CurveParams &cp, float *sm1, int cx0, int cy0, int fx0, int fy0) {
+  constexpr int NPAIR = (P1W + 1) / 2;  // 34 column pairs per patch row: even column -> word kx, odd column -> word 34 + kx
+  const float *src = a.in + (int64_t)(fy0 - a.max_supp) * a.width + (fx0 - a.max_supp);
+  for (int i = threadIdx.x; i < P1H * NPAIR; i += kThreads) {
+    const int ly = i / NPAIR, kx = i - ly * NPAIR;
+    const float *row = src + (int64_t)ly * a.width + 2 * kx;
+    float *cell = sm1 + ly * P1S + kx;
+    const float ve = h2f(f2h(__ldg(row)));
+    cell[G * P1H * P1S] = ve;
+#pragma unroll
+    for (int k = 0; k < G; k++) cell[k * P1H * P1S] = h2f(f2h(curve(ve, (k + 0.5f) / (float)G, cp)));
+    if (kx < NPAIR - 1) {  // the patch has 67 columns: the last pair has no odd member
+      const float vo = h2f(f2h(__ldg(row + 1)));
+      cell[34 + G * P1H * P1S] = vo;
+#pragma unroll
+      for (int k = 0; k < G; k++) cell[34 + k * P1H * P1S] = h2f(f2h(curve(vo, (k + 0.5f) / (float)G, cp)));
+    }
+  }
+  __syncthreads();
+  const float w0 = 1.0f / 16.0f, w1 = 4.0f / 16.0f, w2 = 6.0f / 16.0f;
+  const int lx = threadIdx.x & 31, rg = (threadIdx.x >> 5) & 3, part = threadIdx.x >> 7;
+  const int k0 = part ? 4 : 0, k1 = part ? NP : 4;  // planes 0 .. 3 / 4 .. 6
+  for (int k = k0; k < k1; k++) {
+    // coarse row 4 rg + r has its stencil centre on patch row 2 (4 rg + r) + 2: fine rows 8 rg + 2 r .. 8 rg + 2 r + 4; the centre
+    // column of coarse column lx is patch column 2 lx + 2: even words lx, lx + 1, lx + 2 and odd words lx, lx + 1
+    const float *e = sm1 + k * P1H * P1S + (8 * rg) * P1S + lx;
+    float h[11];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+      const float *p = e + r * P1S;
+      h[r] = fmaf(p[2], w0, fmaf(p[35], w1, fmaf(p[1], w2, fmaf(p[34], w1, p[0] * w0))));
+    }
+    __half *o = a.coarse[k] + (int64_t)(cy0 + 4 * rg) * a.cw + cx0 + lx;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      o[(int64_t)r * a.cw] = f2h(fmaf(h[2 * r + 4], w0, fmaf(h[2 * r + 3], w1, fmaf(h[2 * r + 2], w2, fmaf(h[2 * r + 1], w1, h[2 * r] * w0)))));
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) reduce1_kernel(const __grid_constant__ Reduce1Args a, const CurveParams cp) {
   extern __shared__ float sm1[];  // [NP][P1H][P1S]
   const int cx0 = blockIdx.x * R1W, cy0 = blockIdx.y * R1H;
   const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
   const int ms = a.max_supp;
+  if (fx0 - ms >= 0 && fy0 - ms >= 0 && fx0 + P1W - ms <= a.width && fy0 + P1H - ms <= a.height && cx0 >= 1 && cy0 >= 1 &&
+      cx0 + R1W <= a.cw - 1 && cy0 + R1H <= a.ch - 1) {
+    reduce1_interior(a, cp, sm1, cx0, cy0, fx0, fy0);
+    return;
+  }
   // patch inside the padded frame and on one side of the image along an axis -> constant along that axis
   const bool in_frame = fx0 >= 0 && fy0 >= 0 && fx0 + P1W <= a.fw && fy0 + P1H <= a.fh;
   const bool flat_x = in_frame && (fx0 + P1W - 1 - ms <= 0 || fx0 - ms >= a.width - 1);
