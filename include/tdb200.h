@@ -281,6 +281,14 @@ int tdb_jpeg_encode(void *coder, const uint8_t *image, int width, int height, in
 int tdb_jpeg_retrieve(void *coder, uint8_t *host_out, size_t capacity, size_t *length, tdb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Per-channel noise estimate: replaces estimate_channel_noise (reference denoise.py:131-158, a conv2d over the whole image +
+ * strided slice + two torch.median) by a sampled kernel and an exact on-device selection.  sigma: device float[3] =
+ * median(|r - median(r)|) / 0.6745 per channel, r = 4-neighbour Laplacian response at every `stride`-th pixel (zero padding).
+ * scratch: tdb_channel_noise_scratch_bytes() bytes.  The result can be passed to tdb_wiener as its `sigmas`.               */
+size_t tdb_channel_noise_scratch_bytes(int width, int height, int stride);
+int tdb_channel_noise(const float *rgb, int width, int height, int stride, void *scratch, float *sigma, tdb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Pipe-throughput probes (csrc/probe.cu): kernels that keep ONLY the FP32 FMA pipe / ONLY the MUFU unit busy, for the
  * denominators of the non-HBM rooflines in bench.py (SURVEY.md 8d asks for FLOP/s beside B/px for the Wiener tiles;
  * the reference has no counterpart).  The caller times the launch with CUDA events; *flops / *ops = the work it does. */

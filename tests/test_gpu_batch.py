@@ -1,0 +1,107 @@
+"""GPU: ImageProcessor.process_batch -- the (N, bytes) batch entry and its CUDA-graph form.
+
+A batch is N image sets of one frame each, i.e. N calls of ImageProcessor.process (reference pipeline/image_processor.py:274-300)
+with the EMA of bounds / metrics carried from frame to frame.  The graph form must be indistinguishable from the eager calls, on the
+capturing call AND on replays with new input.  "Indistinguishable" = what two eager runs of the same frame guarantee: the Wiener
+overlap-add accumulates with float atomics whose order varies from run to run (as in the reference, denoise.cu:173-177), so a
+uint8 sample may differ by one LSB on a few samples per million; the tests allow 1 LSB on at most 1e-4 of the samples and 1e-6 on
+the EMA state."""
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def td():
+  import torch
+  assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+  import torch_darktable
+  return torch_darktable
+
+
+def make_processor(td, w, h, ma, transform='rotate_270', debayer='rcd'):
+  import torch
+  from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
+  from torch_darktable.pipeline.config import Debayer, ToneMapper
+  settings = ImageProcessingSettings(debayer=Debayer[debayer], tone_mapping=ToneMapper.adaptive_aces, enable_denoise=True, enable_bilateral=True,
+                                     postprocess=True, tone_gamma=1.5, tone_intensity=2.0, light_adapt=0.8, vibrance=0.5, moving_average=ma)
+  return ImageProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, torch.device('cuda:0'), (1.8, 1.0, 2.1),
+                        ImageTransform[transform])
+
+
+def assert_same(got, want, what=''):
+  import torch
+  d = (got.to(torch.int16) - want.to(torch.int16)).abs()
+  assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 1e-4, f'{what}: max {int(d.max())} LSB, {float((d > 0).float().mean()):.2e} of the samples differ'
+
+
+def frames_of(h, w, seeds, gain=1.0):
+  import torch
+  fr = []
+  for s in seeds:
+    cfa = synth.mosaic(synth.scene_rgb(h, w, s), 'RGGB') * (gain * (0.6 + 0.1 * (s % 5)))  # exposures differ: the EMA has something to do
+    fr.append(synth.pack12(np.floor(np.clip(cfa, 0, 1) * 4095.0 + 0.5).astype(np.uint16)))
+  return torch.from_numpy(np.stack(fr)).cuda()
+
+
+@pytest.mark.parametrize('h,w,transform', [(192, 256, 'rotate_270'), (250, 372, 'none')])
+@pytest.mark.parametrize('ma', [1.0, 0.3])
+def test_batch_graph_equals_eager_calls(td, h, w, transform, ma):
+  import torch
+  batches = [frames_of(h, w, range(10 * b, 10 * b + 4)) for b in range(3)]
+  eager = make_processor(td, w, h, ma, transform)
+  want = [[eager.process(f, 'cam') for f in batch] for batch in batches]
+  want_state = (eager.bounds.clone(), eager.metrics.clone())
+
+  graphed = make_processor(td, w, h, ma, transform)
+  for b, batch in enumerate(batches):  # call 0 runs eagerly and captures, calls 1 and 2 replay with new input
+    got = graphed.process_batch(batch, 'cam', graph=True)
+    assert got.shape[0] == 4 and got.dtype == torch.uint8
+    for i in range(4):
+      assert_same(got[i], want[b][i], f'batch {b} frame {i}: graph vs eager')
+  assert graphed._batch_graph is not None
+  assert torch.allclose(graphed.bounds, want_state[0], atol=1e-6) and torch.allclose(graphed.metrics, want_state[1], atol=1e-6)
+
+  plain = make_processor(td, w, h, ma, transform)
+  for b, batch in enumerate(batches):
+    got = plain.process_batch(batch, 'cam', graph=False)
+    for i in range(4):
+      assert_same(got[i], want[b][i], f'batch {b} frame {i}: batch vs per-frame calls')
+
+
+def test_batch_input_buffer_is_read_in_place(td):
+  """Filling the graph's own input buffer saves the device-to-device copy; the output buffer is reused by the next call."""
+  import torch
+  h, w = 192, 256
+  proc = make_processor(td, w, h, 1.0)
+  first = frames_of(h, w, [1, 2])
+  out0 = proc.process_batch(first, 'cam').clone()
+  buf = proc.batch_input_buffer(2)
+  assert buf.data_ptr() == proc._batch_graph[2].data_ptr()
+  second = frames_of(h, w, [3, 4])
+  buf.copy_(second)
+  out1 = proc.process_batch(buf, 'cam')
+  ref = make_processor(td, w, h, 1.0)
+  assert_same(out1[0], ref.process(second[0], 'cam')), assert_same(out1[1], ref.process(second[1], 'cam'))
+  assert not torch.equal(out0, out1)
+  with pytest.raises(Exception):
+    proc.process_batch(second[:, :-3], 'cam')
+
+
+def test_state_from_stage_path_carries_into_the_fused_path(td):
+  """bounds / metrics set by the stage-by-stage composite (new tensors) are picked up by the in-place state of the fused path."""
+  import torch
+  h, w = 192, 256
+  fr = frames_of(h, w, [5, 6, 7])
+  a, b = make_processor(td, w, h, 0.4), make_processor(td, w, h, 0.4)
+  a.process_image_set_by_stage({'cam': fr[0]})
+  b.process_image_set({'cam': fr[0]})
+  ra = a.process_image_set({'cam': fr[1]})['cam']
+  rb = b.process_image_set({'cam': fr[1]})['cam']
+  d = (ra.to(torch.int16) - rb.to(torch.int16)).abs()
+  assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 1e-3
+  assert torch.allclose(a.bounds, b.bounds, atol=2e-6) and torch.allclose(a.metrics, b.metrics, atol=2e-5)

@@ -88,7 +88,13 @@ def create_wiener(device: torch.device, image_size: tuple[int, int], *, overlap:
 
 @beartype
 def estimate_channel_noise(image: torch.Tensor, stride: int = 8) -> torch.Tensor:
-  """Per-channel sigma from the MAD of a 4-neighbour Laplacian response, sampled every `stride` pixels."""
+  """Per-channel sigma from the MAD of a 4-neighbour Laplacian response, sampled every `stride` pixels.
+
+  CUDA float32 images take the fused path (csrc/noise.cu: the response is evaluated at the sampled pixels only and the two medians
+  are exact on-device selections; the (3,) result stays on the device and can be handed to `Wiener.process` as its noise).  Other
+  tensors run the reference's device-agnostic torch code (denoise.py:131-158) as it is."""
+  if image.is_cuda and image.dtype == torch.float32 and image.dim() == 3 and image.size(2) == 3:
+    return extension.channel_noise(image.contiguous(), stride)
   kernel = torch.tensor([[0, -1, 0], [-1, 4, -1], [0, -1, 0]], dtype=image.dtype, device=image.device)
   chw = image.permute(2, 0, 1).unsqueeze(0)
   response = torch.conv2d(chw, kernel.expand(3, 1, 3, 3).contiguous(), groups=3, padding=1)[0, :, ::stride, ::stride].flatten(1)

@@ -606,9 +606,19 @@ _TM = {'reinhard': 0, 'aces': 1, 'adaptive_aces': 2, 'linear': 3}
 _TF = {'none': 0, 'rotate_90': 1, 'rotate_180': 2, 'rotate_270': 3, 'transpose': 4, 'flip_horiz': 5, 'flip_vert': 6, 'transverse': 7}
 
 
+def _tonemap_out(out: torch.Tensor | None, h: int, w: int, transform: str, device) -> torch.Tensor:
+  shape = (w, h, 3) if transform in ('rotate_90', 'rotate_270', 'transpose') else (h, w, 3)
+  if out is None:
+    return torch.empty(shape, dtype=torch.uint8, device=device)
+  _require(out.is_cuda and out.dtype == torch.uint8 and tuple(out.shape) == shape and out.is_contiguous(),
+           f'out must be a contiguous uint8 CUDA tensor of shape {shape}')
+  return out
+
+
 def tonemap(image: torch.Tensor, op: str, metrics: torch.Tensor | None, params, matrix: torch.Tensor | None = None,
-            transform: str = 'none') -> torch.Tensor:
-  """Fused [3x3 matrix] -> tone map -> gamma -> vibrance -> uint8 [-> rotate/flip].  Returns the transformed (H', W', 3)."""
+            transform: str = 'none', out: torch.Tensor | None = None) -> torch.Tensor:
+  """Fused [3x3 matrix] -> tone map -> gamma -> vibrance -> uint8 [-> rotate/flip].  Returns the transformed (H', W', 3);
+  `out` (optional) receives it in place (a slot of a batch buffer, see ImageProcessor.process_batch)."""
   _check_image(image)
   src = image.contiguous()
   h, w = src.size(0), src.size(1)
@@ -619,8 +629,7 @@ def tonemap(image: torch.Tensor, op: str, metrics: torch.Tensor | None, params, 
     metrics = None
   if matrix is not None:
     matrix = matrix.to(device=src.device, dtype=torch.float32).contiguous()
-  swap = transform in ('rotate_90', 'rotate_270', 'transpose')
-  out = torch.empty((w, h, 3) if swap else (h, w, 3), dtype=torch.uint8, device=src.device)
+  out = _tonemap_out(out, h, w, transform, src.device)
   with torch.cuda.device(src.device):
     check(lib.tdb_tonemap(_ptr(src), _ptr(out), w, h, _TM[op], _ptr(metrics), params.gamma, params.intensity, params.light_adapt,
                           params.vibrance, _ptr(matrix), _TF[transform], _stream(src.device)))
@@ -673,6 +682,18 @@ class Wiener(_Workspace):
       check(lib.tdb_wiener_log_luminance(_ptr(rgb), _ptr(out), _ptr(scratch), w, h, self._tile, self._overlap, float(noise), float(eps),
                                          _stream(rgb.device)))
     return out
+
+
+def channel_noise(image: torch.Tensor, stride: int = 8) -> torch.Tensor:
+  """Per-channel noise sigma (3,) of an (H, W, 3) float32 CUDA image, on the device (csrc/noise.cu)."""
+  _rgb_image(image)
+  _require(stride >= 1, 'stride must be positive')
+  h, w = image.size(0), image.size(1)
+  scratch = torch.empty(lib.tdb_channel_noise_scratch_bytes(w, h, int(stride)), dtype=torch.uint8, device=image.device)
+  sigma = torch.empty(3, dtype=torch.float32, device=image.device)
+  with torch.cuda.device(image.device):
+    check(lib.tdb_channel_noise(_ptr(image), w, h, int(stride), _ptr(scratch), _ptr(sigma), _stream(image.device)))
+  return sigma
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -852,11 +873,11 @@ class FramePipeline:
                                    self._s()))
 
   def slice_tonemap(self, rgb: torch.Tensor, bilateral: 'Bilateral', detail: float, op: str, metrics: torch.Tensor | None, params,
-                    matrix: torch.Tensor | None = None, transform: str = 'none', lab_input: bool = False) -> torch.Tensor:
+                    matrix: torch.Tensor | None = None, transform: str = 'none', lab_input: bool = False,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
     _rgb_image(rgb)
     h, w = self._height, self._width
-    swap = transform in ('rotate_90', 'rotate_270', 'transpose')
-    out = torch.empty((w, h, 3) if swap else (h, w, 3), dtype=torch.uint8, device=rgb.device)
+    out = _tonemap_out(out, h, w, transform, rgb.device)
     with torch.cuda.device(self._device):
       check(lib.tdb_bilateral_slice_tonemap(_ptr(rgb), int(lab_input), _ptr(bilateral._grid_scratch()), _ptr(out), w, h, bilateral._sigma_s,
                                             bilateral._sigma_r, float(detail), _TM[op], _ptr(None if op == 'aces' else metrics), params.gamma,
@@ -886,7 +907,7 @@ extension = SimpleNamespace(
   # fused additions (not in the reference binding)
   unpack12_wb=unpack12_wb, demosaic_packed=demosaic_packed, normalize=normalize, lerp=lerp, tonemap=tonemap,
   FramePipeline=FramePipeline, image_metric_sums=image_metric_sums, metrics_from_sums=metrics_from_sums, green_sums=green_sums, green_eq_apply=green_eq_apply,
-  launch_count=launch_count,
+  launch_count=launch_count, channel_noise=channel_noise,
 )
 
 __all__ = ['extension']
