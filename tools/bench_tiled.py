@@ -29,6 +29,7 @@ def main():
   ap.add_argument('--steps', type=int, default=3)
   ap.add_argument('--warmup', type=int, default=2)
   ap.add_argument('--sigma-s', type=float, default=8.0)
+  ap.add_argument('--breakdown', action='store_true', help='one more frame with a CUDA event after every phase: per-phase ms, max over the ranks')
   args = ap.parse_args()
   rank, local, world = int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 
@@ -87,6 +88,18 @@ def main():
     t = torch.tensor([ms], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+  phases = None
+  if args.breakdown:
+    proc.profile = True
+    barrier()
+    proc.process(own)
+    local = proc.breakdown()
+    proc.profile = False
+    names = list(local)
+    t = torch.tensor([local[k] for k in names], device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    phases = {k: round(float(v), 3) for k, v in zip(names, t.tolist())}
   checksum = int(out.to(torch.int64).sum().item())
   if world > 1:
     t = torch.tensor([checksum], device=dev)
@@ -100,8 +113,8 @@ def main():
       'config': {'workload': f'one {w}x{h} ({w * h / 1e6:.0f} MP) 12-bit packed RGGB frame, RCD + postprocess + Wiener + bilateral '
                              f'(sigma_s {args.sigma_s:g}) + adaptive ACES', 'bands': world, 'halo_rows': halo if world > 1 else 0,
                  'halo_bytes_per_neighbour': halo * w * 3 // 2 if world > 1 else 0,
-                 'collectives': 'packed halo rows by NCCL send/recv; 3 all-reduces of <= 6 floats' if world > 1 else 'none'},
-      'checksum_u8_sum': checksum, 'peak_mem_gb': round(torch.cuda.max_memory_allocated() / 2**30, 2)}), flush=True)
+                 'collectives': 'packed halo rows by NCCL send/recv; one all-gather + one all-reduce of 6 floats' if world > 1 else 'none'},
+      'phases_ms_max_over_ranks': phases, 'checksum_u8_sum': checksum, 'peak_mem_gb': round(torch.cuda.max_memory_allocated() / 2**30, 2)}), flush=True)
   if world > 1:
     dist.destroy_process_group()
 

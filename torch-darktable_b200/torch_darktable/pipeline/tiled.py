@@ -233,6 +233,8 @@ class TiledFrameProcessor:
     self.white_balance = torch.tensor(white_balance, dtype=torch.float32, device=device) if white_balance is not None else None
     self.bounds: torch.Tensor | None = None   # EMA state, identical on every rank
     self.metrics: torch.Tensor | None = None
+    self.profile = False                      # record a CUDA event after every phase of `process` (see `breakdown`)
+    self._events: list | None = None
     if self.width % 2:
       raise ValueError('frame width must be even')
     if settings.enable_bilateral:
@@ -241,6 +243,22 @@ class TiledFrameProcessor:
         raise ValueError('the bilateral grid of the full frame saturates in y (height / sigma_s > 3000): not reproducible per band')
       if abs(self.band.padded[0] / s - round(self.band.padded[0] / s)) > 1e-6:
         raise ValueError(f'bil_sigma_spatial={s} does not divide the band origin {self.band.padded[0]}: the grid phase would shift')
+
+  def _mark(self, name: str):
+    if self._events is not None:
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      self._events.append((name, ev))
+
+  def breakdown(self) -> dict[str, float]:
+    """Milliseconds per phase of the last `process` call made with `profile = True` (synchronises the device)."""
+    if not self._events:
+      return {}
+    torch.cuda.synchronize(self.device)
+    out: dict[str, float] = {}
+    for (_, a), (name, b) in zip(self._events, self._events[1:]):
+      out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    return out
 
   @property
   def row_bytes(self) -> int:
@@ -293,6 +311,7 @@ class TiledFrameProcessor:
     rgb = self.td.demosaic_packed(packed, size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
                                   white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
     smoothed, raw = frame.smooth_band(post, rgb, lo, hi)
+    self._mark('demosaic + smoothing')
     stats = col.all_gather(raw)  # (world, 6): one collective for the green sums, the minima and the maxima
     sums = stats[:, 0:2].sum(0)
     mins, maxs = stats[:, [2, 4]].min(0).values, stats[:, [3, 5]].max(0).values
@@ -305,6 +324,7 @@ class TiledFrameProcessor:
     hi_v = torch.where(have_g1, torch.maximum(maxs[1], torch.maximum(maxs[0] * ratio[0], zero)), maxs[1])
     bounds = torch.stack([lo_v, hi_v])
     self.bounds = lerp(self.bounds if self.bounds is not None else bounds, bounds, s.moving_average)
+    self._mark('all-gather of the band statistics + bounds')
 
     image = frame.prepare(smoothed, ratio, self.bounds, wiener)
     if wiener is not None:
@@ -312,9 +332,12 @@ class TiledFrameProcessor:
     elif bil is not None:
       frame.bilateral_grid(bil, image)
     lab = wiener is not None and bil is not None
-    msums = col.all_reduce(frame.metric_sums_band(image, bil, s.bilateral, lo, hi, lab_input=lab), 'sum')
+    local_sums = frame.metric_sums_band(image, bil, s.bilateral, lo, hi, lab_input=lab)
+    self._mark('prepare + Wiener + bilateral grid + metric sums')
+    msums = col.all_reduce(local_sums, 'sum')
     metrics = extension.metrics_from_sums(msums)
     self.metrics = lerp(self.metrics if self.metrics is not None else metrics, metrics, s.moving_average)
+    self._mark('all-reduce of the metric sums + metrics')
 
     params = self.td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
     op = _TONEMAP_OPS[s.tone_mapping]
@@ -322,14 +345,19 @@ class TiledFrameProcessor:
       out = frame.slice_tonemap(image, bil, s.bilateral, op, self.metrics, params, None, 'none', lab_input=lab)
     else:
       out = extension.tonemap(image, op, None if op == 'aces' else self.metrics, params, None, 'none')
-    return self._own(out).contiguous()
+    own = self._own(out).contiguous()
+    self._mark('slice + tone map + crop')
+    return own
 
   def process(self, own_packed_rows: torch.Tensor) -> torch.Tensor:
     """own_packed_rows: uint8 tensor with the packed bytes of this rank's rows.  Returns the uint8 (rows, W, 3) sRGB band."""
     b, s, ops, col = self.band, self.settings, self.ops, self.collective
     if own_packed_rows.numel() != (b.y1 - b.y0) * self.row_bytes:
       raise ValueError(f'expected {(b.y1 - b.y0) * self.row_bytes} packed bytes for rows {b.y0}..{b.y1}, got {own_packed_rows.numel()}')
+    self._events = [] if self.profile else None
+    self._mark('start')
     packed = col.exchange_halos(self._fill_padded(own_packed_rows), self.row_bytes, b)
+    self._mark('halo exchange')
     p0, p1 = b.padded
     size = (self.width, p1 - p0)
     if self.fused:
