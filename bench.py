@@ -321,7 +321,8 @@ def leg_tiled_200mp(torch, dist, td, dev, rank, world, steps=3):
   col = DistCollective() if world > 1 else ThreadCollective(ThreadCollective.Hub(1), 0)
   proc = TiledFrameProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, (1.8, 1.0, 2.1), col)
   y0, y1 = proc.owned_rows
-  own = device_packed_scene(torch, td, h, w, 7, dev, y0, y1, h)
+  own = proc.own_rows_buffer()  # the rank's rows live in the padded band buffer: no band-sized copy per frame
+  own.copy_(device_packed_scene(torch, td, h, w, 7, dev, y0, y1, h))
   out = [None]
 
   def step():

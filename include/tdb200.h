@@ -253,6 +253,13 @@ int tdb_postprocess_deferred_band(const float *in, float *out, void *scratch, in
 int tdb_metrics_sliced_band(const float *rgb, int lab_input, const void *bilateral_scratch, int width, int height, float sigma_s,
                             float sigma_r, float detail, int stride, float min_gray, void *frame_state, int row_lo, int row_hi,
                             float *raw_sums, tdb_stream_t stream);
+/* Where the ranks' partial statistics of a split frame meet (after the all-gather of the six raw_out floats of every rank, and after
+ * the all-reduce of the six metric sums): ratio, bounds of the equilibrated image and metrics with their moving averages, one
+ * single-thread kernel each.  gathered: device float[world][6] in rank order.  prev_* == NULL: no previous value (first frame);
+ * bounds_out / metrics_out may alias prev_* (updated in place).                                                                */
+int tdb_band_stats_finish(const float *gathered, int world, const float *prev_bounds, float moving_average, float *bounds_out, float *ratio_out,
+                          tdb_stream_t stream);
+int tdb_band_metrics_finish(const float *sums, const float *prev_metrics, float moving_average, float *metrics_out, tdb_stream_t stream);
 /* the first half of tdb_bilateral_rgb: zero + splat + blur, leaving the blurred grid in scratch                          */
 int tdb_bilateral_grid_rgb(const float *rgb, void *scratch, int width, int height, float sigma_s, float sigma_r,
                            tdb_stream_t stream);

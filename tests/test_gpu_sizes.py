@@ -217,3 +217,44 @@ def test_host_frame_runner_streams_batches():
   for i, (got, ref) in enumerate(zip(outs, want)):
     d = (got.to(torch.int16) - ref.to(torch.int16)).abs()
     assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 1e-4, f'frame {i}: max {int(d.max())} LSB, {float((d > 0).float().mean()):.2e} differ'
+
+
+# ---- repeatability of the asynchronous / last-CTA paths (compute-sanitizer is closed on this pool: a race has to show up as a
+# run-to-run difference) ------------------------------------------------------------------------------------------------------
+def test_smoothing_bulk_copy_path_is_repeatable():
+  """PostProcess with 3 smoothing passes stages its interior patches with cp.async.bulk + mbarrier (csrc/postprocess.cu) and reduces the
+  green sums / bounds through a last-CTA ticket (csrc/frame_state.cuh): sixteen runs on the same 516 x 1100 input (several waves of
+  CTAs) must be bit-identical -- medians are exact and the partials are summed in a fixed order."""
+  import torch
+  import torch_darktable as td
+  h, w = 516, 1100
+  rng = np.random.default_rng(3)
+  rgb = torch.from_numpy((synth.scene_rgb(h, w, 11) + rng.normal(0, 0.02, (h, w, 3))).astype(np.float32)).cuda()
+  pp = td.PostProcess(torch.device('cuda:0'), (w, h), td.BayerPattern.RGGB, color_smoothing_passes=3, green_eq_global=True)
+  first = pp.process(rgb).clone()
+  for _ in range(15):
+    assert torch.equal(pp.process(rgb), first)
+
+
+def test_frame_statistics_tickets_are_repeatable():
+  """The fused frame pipeline's statistics (green ratio, bounds, metrics) come out of last-CTA ticket reductions: the same frame through
+  a fresh processor sixteen times gives identical bounds and metrics (the metrics are sums of the Wiener output, whose float atomics
+  may reorder: 1e-6), and the strip RCD (TMA-staged rows, mbarrier hand-over) gives bit-identical RGB."""
+  import torch
+  import torch_darktable as td
+  from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
+  from torch_darktable.pipeline.config import Debayer, ToneMapper
+  h, w = 516, 1100
+  frame = torch.from_numpy(synth.packed_frame(h, w, seed=21)).cuda()
+  settings = ImageProcessingSettings(debayer=Debayer.rcd, tone_mapping=ToneMapper.adaptive_aces, enable_denoise=True, enable_bilateral=True,
+                                     postprocess=True, tone_gamma=1.5, tone_intensity=2.0, light_adapt=0.8, vibrance=0.5, moving_average=1.0)
+  ref_rgb = td.demosaic_packed(frame, (w, h), td.BayerPattern.RGGB, method='rcd')
+  bounds, metrics = [], []
+  for _ in range(16):
+    assert torch.equal(td.demosaic_packed(frame, (w, h), td.BayerPattern.RGGB, method='rcd'), ref_rgb)
+    proc = ImageProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, torch.device('cuda:0'), None, ImageTransform.none)
+    proc.process(frame, 'cam')
+    bounds.append(proc.bounds.clone()), metrics.append(proc.metrics.clone())
+  for b, m in zip(bounds[1:], metrics[1:]):
+    assert torch.equal(b, bounds[0])
+    assert torch.allclose(m, metrics[0], atol=1e-6, rtol=0)

@@ -63,7 +63,8 @@ def main():
   cfa = 0.15 + 0.5 * (xs / w * 0.6 + ys / h * 0.4) + 0.12 * torch.sin((xs + 0.5 * ys) * (6.2831853 / 37.0)) \
       + 0.1 * torch.sin((ys - 0.3 * xs) * (6.2831853 / 211.0)) + 0.03 * noise
   del noise
-  own = td.encode(cfa.clamp_(0.02, 1.0).reshape(-1))
+  own = proc.own_rows_buffer()  # the rank's rows go straight into the padded band buffer: no band-sized copy per frame
+  own.copy_(td.encode(cfa.clamp_(0.02, 1.0).reshape(-1)))
   del cfa, ys, xs
   torch.cuda.empty_cache()
 

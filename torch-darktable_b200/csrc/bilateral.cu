@@ -119,7 +119,10 @@ constexpr int kMaxAxisPx = 1024;  // pixels a CTA's columns can span along one a
 // ones of the general path bit for bit)
 template <int kBY, bool kTables, bool kS2 = false>
 __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__restrict__ lum, float *__restrict__ out, int width, int height,
-                                                              GridDims g, float sigma_s, float sigma_r) {
+                                                              GridDims g, float sigma_s, float sigma_r, int pitch, const float *__restrict__ pile_x,
+                                                              const float *__restrict__ pile_y) {
+  // width / height: the pixels the gather may visit (for a saturating grid only those in front of the piles, see pile_rows_kernel);
+  // pitch: floats per image row; pile_x[j][z] / pile_y[i][z]: what the piled pixels add to the last cell column / row (or null)
   constexpr int PY = kBY + 4;
   extern __shared__ float sm[];
   float *cells = sm;                     // [z][PY][GPX] splatted columns of this CTA
@@ -167,15 +170,23 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
     const int lj = col / GPX, li = col - lj * GPX;
     const int i = ci0 + li, j = cj0 + lj;
     float *bins = cells + lj * GPX + li;
-    for (int z = 0; z < g.z; z++) bins[z * ZS] = 0.0f;
-    if (i < 0 || j < 0 || i >= g.x || j >= g.y) continue;
+    const bool in_grid = i >= 0 && j >= 0 && i < g.x && j < g.y;
+    for (int z = 0; z < g.z; z++) {
+      float v = 0.0f;
+      if (pile_x && in_grid) {
+        if (i == g.x - 1) v += __ldg(pile_x + j * g.z + z);
+        if (j == g.y - 1) v += __ldg(pile_y + i * g.z + z);
+      }
+      bins[z * ZS] = v;
+    }
+    if (!in_grid) continue;
     if (kS2) {
 #pragma unroll
       for (int dy = -1; dy <= 1; dy++) {
         const int y = 2 * j + dy;
         if (y < 0 || y >= height) continue;
         const float wy = dy == 0 ? 1.0f : 0.5f;
-        const float *row = lum + (int64_t)y * width + 2 * i;
+        const float *row = lum + (int64_t)y * pitch + 2 * i;
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++) {
           if (2 * i + dx < 0 || 2 * i + dx >= width) continue;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
     for (int ty = ry.x; ty <= ry.y; ty++) {
       const AxisSample sy = kTables ? ax_y[ty] : axis_sample(ybase + ty, sigma_s, g.y);
       const float wy = sy.i == j ? 1.0f - sy.f : sy.f;
-      const float *row = lum + (int64_t)(ybase + ty) * width + xbase;
+      const float *row = lum + (int64_t)(ybase + ty) * pitch + xbase;
 #pragma unroll 4
       for (int tx = rx.x; tx <= rx.y; tx++) {
         const AxisSample sx = kTables ? ax_x[tx] : axis_sample(xbase + tx, sigma_s, g.x);
@@ -235,6 +246,74 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
       if (z < g.z) p2 = b[0] * w0 + w1 * (b[BX] + b[-BX]) + w2 * (b[2 * BX] + b[-2 * BX]);
       if (z >= 2) o[plane * (z - 2)] = d1 * (p1 - m1) + d2 * (p2 - m2);
       m2 = m1, m1 = c0, c0 = p1, p1 = p2;
+    }
+  }
+}
+
+// ---- saturating grids ------------------------------------------------------------------------------------------------------------
+// The reference clamps the cell count to 3000 per axis but keeps sampling with the RAW sigma_s (bilateral.cu:273-299 + :71-86): at
+// 8192 px and sigma_s = 2 every pixel with x >= 6000 has the clamped coordinate g.x - 1, i.e. lower cell g.x - 2 with fraction 1, and
+// lands in the LAST cell column with x weight 1 (likewise rows y >= 4500; the corner cell collects 3.6 M pixels).  The scatter with
+// global atomics serialises on those cells (2.9 ms of 3.3 ms at 50 MP).  Instead: the piled pixels are reduced separately into
+//   pile_x[j][z]  everything the pixels x >= x_pile add to cell column g.x - 1   (one CTA per image row: its pixels share the two cell
+//                 rows and y weights, so the CTA sums their z contributions privately and issues 2 g.z atomics)
+//   pile_y[i][z]  what the pixels y >= y_pile, x < x_pile add to cell row g.y - 1 (one CTA per 32 image columns, summed down the rows)
+// and the gather kernel, restricted to the pixels in front of the piles, seeds the bins of the last column / row with them.  Same
+// weights as the scatter (w_x * w_y * w_z / sigma_s^2); only the order of the additions differs, which was arbitrary before.
+__global__ void __launch_bounds__(kThreads) pile_rows_kernel(const float *__restrict__ lum, float *__restrict__ pile_x, int width, int height,
+                                                             int x_pile, GridDims g, float sigma_s, float sigma_r) {
+  extern __shared__ float psm[];  // [g.z][kThreads] private z bins, then the per-z totals
+  const int y = blockIdx.x;
+  for (int z = 0; z < g.z; z++) psm[z * kThreads + threadIdx.x] = 0.0f;
+  const float contrib = 1.0f / (sigma_s * sigma_s);
+  const float *row = lum + (int64_t)y * width;
+  for (int x = x_pile + threadIdx.x; x < width; x += kThreads) {
+    const float gz = fminf(fmaxf(__ldg(row + x) / sigma_r, 0.0f), (float)(g.z - 1));
+    const int iz = min((int)gz, g.z - 2);
+    const float fz = gz - (float)iz;
+    psm[iz * kThreads + threadIdx.x] += (1.0f - fz) * contrib;
+    psm[(iz + 1) * kThreads + threadIdx.x] += fz * contrib;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const AxisSample sy = axis_sample(y, sigma_s, g.y);
+  for (int z = warp; z < g.z; z += kThreads / 32) {
+    float v = 0.0f;
+    for (int t = lane; t < kThreads; t += 32) v += psm[z * kThreads + t];
+    v = warp_sum(v);
+    if (lane == 0 && v != 0.0f) {
+      if (sy.f != 1.0f) atomicAdd(pile_x + sy.i * g.z + z, (1.0f - sy.f) * v);
+      if (sy.f != 0.0f) atomicAdd(pile_x + (sy.i + 1) * g.z + z, sy.f * v);
+    }
+  }
+}
+__global__ void __launch_bounds__(kThreads) pile_columns_kernel(const float *__restrict__ lum, float *__restrict__ pile_y, int width, int height,
+                                                                int x_pile, int y_pile, GridDims g, float sigma_s, float sigma_r) {
+  extern __shared__ float psm[];  // [g.z][8 row lanes][32 columns]
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + cx;
+  for (int z = 0; z < g.z; z++) psm[z * kThreads + threadIdx.x] = 0.0f;
+  const float contrib = 1.0f / (sigma_s * sigma_s);
+  if (x < x_pile) {
+    for (int y = y_pile + ry; y < height; y += kThreads / 32) {
+      const float gz = fminf(fmaxf(__ldg(lum + (int64_t)y * width + x) / sigma_r, 0.0f), (float)(g.z - 1));
+      const int iz = min((int)gz, g.z - 2);
+      const float fz = gz - (float)iz;
+      psm[iz * kThreads + threadIdx.x] += (1.0f - fz) * contrib;
+      psm[(iz + 1) * kThreads + threadIdx.x] += fz * contrib;
+    }
+  }
+  __syncthreads();
+  if (ry == 0 && x < x_pile) {
+    const AxisSample sx = axis_sample(x, sigma_s, g.x);
+    for (int z = 0; z < g.z; z++) {
+      float v = 0.0f;
+#pragma unroll
+      for (int r = 0; r < kThreads / 32; r++) v += psm[z * kThreads + r * 32 + cx];
+      if (v != 0.0f) {
+        if (sx.f != 1.0f) atomicAdd(pile_y + sx.i * g.z + z, (1.0f - sx.f) * v);
+        if (sx.f != 0.0f) atomicAdd(pile_y + (sx.i + 1) * g.z + z, sx.f * v);
+      }
     }
   }
 }
@@ -304,8 +383,12 @@ int bilateral_build_grid(void *scratch, const float *lum, int width, int height,
                          cudaStream_t s) {
   // the gather needs every pixel to feed the two cells around p / sigma_s: no saturation at the last cell (grid_dims clamps
   // the cell count to 3000 per axis), and a bounded number of pixels per cell
-  const bool gather = sigma_s >= 1.0f && (width - 1) / sigma_s <= (float)(g.x - 1) && (height - 1) / sigma_s <= (float)(g.y - 1) &&
-                      (GPX + 1) * sigma_s + 8.0f <= (float)kMaxAxisPx;
+  // pixels at or beyond these coordinates have the clamped cell coordinate g.x - 1 (g.y - 1): they pile up in the last cell column (row)
+  const int x_pile = (int)fminf((float)width, ceilf((float)(g.x - 1) * sigma_s)), y_pile = (int)fminf((float)height, ceilf((float)(g.y - 1) * sigma_s));
+  const bool piled = x_pile < width || y_pile < height;
+  // the gather needs a bounded number of pixels per cell: true in front of the piles
+  const bool gather = sigma_s >= 1.0f && (GPX + 1) * sigma_s + 8.0f <= (float)kMaxAxisPx && x_pile >= 1 && y_pile >= 1 &&
+                      (!piled || (size_t)g.z * kThreads * sizeof(float) <= 48 * 1024);  // (the pile kernels keep g.z x 256 private bins)
   if (gather) {
     static DeviceOnce attr;
     attr.run([&] {
@@ -314,15 +397,31 @@ int bilateral_build_grid(void *scratch, const float *lum, int width, int height,
       cudaFuncSetAttribute(grid_build_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * 4);
     });
     float *blurred = static_cast<float *>(scratch) + (size_t)g.x * g.y * g.z;
+    float *pile_x = nullptr, *pile_y = nullptr;
+    if (piled) {  // the unused splat-grid half of the scratch holds the piles
+      pile_x = static_cast<float *>(scratch), pile_y = pile_x + (size_t)g.y * g.z;
+      cudaMemsetAsync(pile_x, 0, (size_t)(g.x + g.y) * g.z * sizeof(float), s);
+      if (int e = check_launch("bilateral_zero_piles")) return e;
+      const size_t psm = (size_t)g.z * kThreads * sizeof(float);
+      if (x_pile < width) {
+        pile_rows_kernel<<<height, kThreads, psm, s>>>(lum, pile_x, width, height, x_pile, g, sigma_s, sigma_r);
+        if (int e = check_launch("bilateral_pile_rows")) return e;
+      }
+      if (y_pile < height) {
+        pile_columns_kernel<<<div_up(x_pile, 32), kThreads, psm, s>>>(lum, pile_y, width, height, x_pile, y_pile, g, sigma_s, sigma_r);
+        if (int e = check_launch("bilateral_pile_columns")) return e;
+      }
+    }
+    const int gw = x_pile, gh = y_pile;  // the gather visits the pixels in front of the piles only
     if (g.z <= 16 && sigma_s == 2.0f) {
       grid_build_kernel<16, true, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(
-          lum, blurred, width, height, g, sigma_s, sigma_r);
+          lum, blurred, gw, gh, g, sigma_s, sigma_r, width, pile_x, pile_y);
     } else if (g.z <= 16 && sigma_s < 3.0f) {
       grid_build_kernel<16, true><<<dim3(div_up(g.x, BX), div_up(g.y, 16)), kThreads, (size_t)g.z * (((20 * GPX + 31) / 32 * 32) + 20 * BX) * sizeof(float), s>>>(
-          lum, blurred, width, height, g, sigma_s, sigma_r);
+          lum, blurred, gw, gh, g, sigma_s, sigma_r, width, pile_x, pile_y);
     } else {
       grid_build_kernel<8, false><<<dim3(div_up(g.x, BX), div_up(g.y, 8)), kThreads, (size_t)g.z * (((12 * GPX + 31) / 32 * 32) + 12 * BX) * sizeof(float), s>>>(
-          lum, blurred, width, height, g, sigma_s, sigma_r);
+          lum, blurred, gw, gh, g, sigma_s, sigma_r, width, pile_x, pile_y);
     }
     return check_launch("bilateral_grid_build");
   }

@@ -84,6 +84,23 @@ void join_side(cudaStream_t main, cudaStream_t side) {
 
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_tensor_map_f32(CUtensorMap *map, const float *plane, int width, int height, int box_w, int box_h) {
+  static const EncodeTiledFn encode = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  memset(map, 0, sizeof *map);
+  if (!encode || !plane || (width & 3) || (reinterpret_cast<uintptr_t>(plane) & 15) || box_w > 256 || box_h > 256 || ((box_w * 4) & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height}, strides[1] = {(cuuint64_t)width * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(plane), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int check_launch(const char *what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (g_timing) mark(what);

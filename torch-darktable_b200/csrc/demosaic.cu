@@ -5,6 +5,8 @@
 //           each a full HBM round trip plus a torch::zeros) by ONE kernel: the CFA patch is staged once (float plane or
 //           12-bit packed bytes), the optional median, the green plane and the red/blue fill all live in shared memory,
 //           and the RGB tile leaves through 128-bit stores.  Algorithmic traffic: 4 (or 1.5) B in + 12 B out per pixel.
+#include <cstdlib>
+
 #include "cfa_tile.cuh"
 
 namespace tdb {
@@ -57,22 +59,44 @@ __device__ __forceinline__ void bil_pixel(const float (&nb)[6][6], int dy, int d
   out[2] = BilTaps<kType, 2, 0>::run(nb, dy, dx, 0.0f) * 0.0625f;
 }
 
+// One CTA-wide tensor-map load of a (box_w x box_h) float patch whose first element is image pixel (px0, py0): thread 0 arms the
+// barrier and issues the copy, everybody waits for its bytes.  Pixels outside the image arrive as zeros.
+__device__ __forceinline__ void stage_patch_tma(float *patch, uint64_t *bar, const CUtensorMap *tmap, int px0, int py0, uint32_t bytes) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_2d(patch, tmap, px0, py0, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// use_tma: `tmap` describes src.cfa (float plane, width % 4 == 0).  Tiles whose 36 x 36 patch lies inside the image take the tensor-map
+// load (SASS UTMALDG); the others need the reference's clamp-to-edge coordinates (bilinear.cu:90), which the TMA unit cannot produce
 template <uint32_t kCode>
 __global__ void __launch_bounds__(kThreads) bilinear_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                            uint32_t filters) {
-  constexpr int P = kTile + 4, S = P;  // even stride: the 64-bit neighbourhood loads stay aligned
-  __shared__ __align__(16) float patch[P * S];
-  __shared__ __align__(16) float outt[kTile * kTile * 3];
+                                                            uint32_t filters, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  // Patch rows hold image columns x0 - 4 .. x0 + 35 (stride 40), of which the stencil reads x0 - 2 .. x0 + 33: a tensor-map box must start
+  // on a 16-byte boundary of its row (a box at x0 - 2 faulted with 'illegal instruction' on B200), and x0 - 4 is one when width % 4 == 0
+  constexpr int P = kTile + 4, S = kTile + 8, X0 = 2;  // X0: patch column of image column x0 - 2
+  extern __shared__ __align__(128) float smem[];
+  float *patch = smem, *outt = smem + P * S;
+  __shared__ uint64_t bar;
   resolve_gains(src, filters);
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  stage_patch<Oob::kClamp, false>(patch, S, x0 - 2, y0 - 2, P, P, src, width, height);
-  __syncthreads();
+  if (use_tma && x0 >= 2 && y0 >= 2 && x0 + kTile + 2 <= width && y0 + kTile + 2 <= height) {
+    stage_patch_tma(patch, &bar, &tmap, x0 - 4, y0 - 2, S * P * sizeof(float));  // the box may reach past the image: zeros nobody reads
+  } else {
+    stage_patch<Oob::kClamp, false>(patch + X0, S, x0 - 2, y0 - 2, P, P, src, width, height);
+    __syncthreads();
+  }
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int qx = tid & 15, qy = tid >> 4;  // one quad per thread, tile origin even in both axes
   float nb[6][6];                          // patch rows 2qy .. 2qy+5, columns 2qx .. 2qx+5
 #pragma unroll
   for (int r = 0; r < 6; r++) {
-    const float2 *row = reinterpret_cast<const float2 *>(patch + (2 * qy + r) * S + 2 * qx);
+    const float2 *row = reinterpret_cast<const float2 *>(patch + X0 + (2 * qy + r) * S + 2 * qx);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const float2 v = row[j];
@@ -185,14 +209,17 @@ __host__ __device__ constexpr int ppg_type(int row, int col, uint32_t filters) {
 
 template <bool kMedian, uint32_t kFilters>
 __global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
-                                                       uint32_t filters, float threshold) {
+                                                       uint32_t filters, float threshold, const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int HC = kMedian ? 6 : 4;             // cfa halo
-  constexpr int PC = kTile + 2 * HC, SC = PC + 1; // cfa patch
+  // cfa patch: PC x PC pixels from image column x0 - HC.  A tensor-map box must start on a 16-byte boundary of its row, so with the
+  // median (HC = 6) the box starts two columns earlier, at x0 - 8, and is 48 wide; XA = patch column of image column x0 - HC
+  constexpr int PC = kTile + 2 * HC, XA = (HC & 3), SC = PC + 2 * XA;
   constexpr int PM = kTile + 8, SM = PM + 1;      // median patch (halo 4)
   constexpr int PT = kTile + 2;                   // tmp patch (halo 1)
-  extern __shared__ __align__(16) float smem[];
-  float *cfa = smem;                                    // PC*SC
-  float *med = cfa + PC * SC;                           // PM*SM (only with the median)
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar;
+  float *cfa = smem + XA;                               // PC rows of SC floats; cfa[ly * SC + lx] = image pixel (x0 - HC + lx, y0 - HC + ly)
+  float *med = smem + PC * SC;                          // PM*SM (only with the median)
   float *tmp = med + (kMedian ? PM * SM : 0);           // PT*PT*3
   float *outt = tmp + PT * PT * 3;                      // kTile*kTile*3 (16-byte aligned by construction below)
   outt = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(outt) + 15) & ~uintptr_t(15));
@@ -200,8 +227,14 @@ __global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__r
   resolve_gains(src, filters);
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  stage_patch<Oob::kZero, false>(cfa, SC, x0 - HC, y0 - HC, PC, PC, src, width, height);
-  __syncthreads();
+  // float plane: every tile, frame tiles included, is ONE tensor-map copy -- the zeros the TMA unit delivers for coordinates outside
+  // the image are the zero-filled halo of the reference (ppg.cu:61,159,270); packed frames are unpacked by the threads
+  if (use_tma) {
+    stage_patch_tma(smem, &bar, &tmap, x0 - HC - XA, y0 - HC, SC * PC * sizeof(float));
+  } else {
+    stage_patch<Oob::kZero, false>(cfa, SC, x0 - HC, y0 - HC, PC, PC, src, width, height);
+    __syncthreads();
+  }
 
   const float *g_in;  // plane the green stage reads, with halo 4 around the tile
   int g_stride;
@@ -308,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) ppg_kernel(CfaSource src, float *__r
 
 template <bool kMedian>
 constexpr size_t ppg_smem_bytes() {
-  constexpr int HC = kMedian ? 6 : 4, PC = kTile + 2 * HC, SC = PC + 1, PM = kTile + 8, SM = PM + 1, PT = kTile + 2;
+  constexpr int HC = kMedian ? 6 : 4, PC = kTile + 2 * HC, SC = PC + 2 * (HC & 3), PM = kTile + 8, SM = PM + 1, PT = kTile + 2;
   return sizeof(float) * (PC * SC + (kMedian ? PM * SM : 0) + PT * PT * 3 + kTile * kTile * 3) + 16;
 }
 
@@ -324,23 +357,30 @@ int check_frame(const char *name, int width, int height) {
 
 int launch_bilinear(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, cudaStream_t s) {
   dim3 block(16, 16), grid(div_up(width, kTile), div_up(height, kTile));
+  CUtensorMap tmap;
+  static const bool tma_on = getenv("TDB_BILINEAR_TMA") == nullptr || atoi(getenv("TDB_BILINEAR_TMA")) != 0;
+  const int tma = tma_on && make_tensor_map_f32(&tmap, src.cfa, width, height, kTile + 8, kTile + 4) ? 1 : 0;
+  constexpr size_t bytes = ((kTile + 4) * (kTile + 8) + kTile * kTile * 3) * sizeof(float);
   switch (quad_code(filters)) {
-    case 0xE4u: bilinear_kernel<0xE4u><<<grid, block, 0, s>>>(src, rgb, width, height, filters); break;
-    case 0x27u: bilinear_kernel<0x27u><<<grid, block, 0, s>>>(src, rgb, width, height, filters); break;
-    case 0xB1u: bilinear_kernel<0xB1u><<<grid, block, 0, s>>>(src, rgb, width, height, filters); break;
-    default: bilinear_kernel<0x8Du><<<grid, block, 0, s>>>(src, rgb, width, height, filters); break;
+    case 0xE4u: bilinear_kernel<0xE4u><<<grid, block, bytes, s>>>(src, rgb, width, height, filters, tmap, tma); break;
+    case 0x27u: bilinear_kernel<0x27u><<<grid, block, bytes, s>>>(src, rgb, width, height, filters, tmap, tma); break;
+    case 0xB1u: bilinear_kernel<0xB1u><<<grid, block, bytes, s>>>(src, rgb, width, height, filters, tmap, tma); break;
+    default: bilinear_kernel<0x8Du><<<grid, block, bytes, s>>>(src, rgb, width, height, filters, tmap, tma); break;
   }
   return check_launch("bilinear5x5_demosaic");
 }
 
 int launch_ppg(const CfaSource &src, float *rgb, int width, int height, uint32_t filters, float median_threshold, cudaStream_t s) {
   dim3 block(16, 16), grid(div_up(width, kTile), div_up(height, kTile));
+  CUtensorMap tmap;
+  const int patch = kTile + 2 * (median_threshold > 0.0f ? 6 : 4), box_w = median_threshold > 0.0f ? patch + 4 : patch;
+  const int tma = make_tensor_map_f32(&tmap, src.cfa, width, height, box_w, patch) ? 1 : 0;
 #define TDB_PPG(CODE)                                                                                                             \
   if (median_threshold > 0.0f) {                                                                                                  \
     cudaFuncSetAttribute(ppg_kernel<true, CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppg_smem_bytes<true>());       \
-    ppg_kernel<true, CODE><<<grid, block, ppg_smem_bytes<true>(), s>>>(src, rgb, width, height, filters, median_threshold / 100.0f); \
+    ppg_kernel<true, CODE><<<grid, block, ppg_smem_bytes<true>(), s>>>(src, rgb, width, height, filters, median_threshold / 100.0f, tmap, tma); \
   } else {                                                                                                                        \
-    ppg_kernel<false, CODE><<<grid, block, ppg_smem_bytes<false>(), s>>>(src, rgb, width, height, filters, 0.0f);                 \
+    ppg_kernel<false, CODE><<<grid, block, ppg_smem_bytes<false>(), s>>>(src, rgb, width, height, filters, 0.0f, tmap, tma);      \
   }
   switch (filters) {
     case TDB_FILTERS_RGGB: TDB_PPG(TDB_FILTERS_RGGB) break;

@@ -11,6 +11,8 @@
 //                    only at the sampled pixels (every stride-th), so that the slice itself can be fused into the tone-map kernel
 //                    and the locally contrasted image never exists in HBM.  The last CTA merges the sums into the image set and
 //                    applies the moving average (image_processor.py:292-294).
+#include <cfloat>
+
 #include "bilateral.cuh"
 #include "frame_state.cuh"
 #include "wiener_layout.cuh"
@@ -194,6 +196,37 @@ __global__ void __launch_bounds__(kThreads) metrics_sliced_kernel(const MetricsA
 }  // namespace
 }  // namespace tdb
 
+namespace tdb {
+namespace {
+// ---- one frame split into row bands (pipeline/tiled.py): the two places where the ranks' partial statistics meet.  Each used to be a
+// dozen tiny torch kernels (sum / min / max over the gathered rows, where, maximum, stack, lerp ...), i.e. ~0.15 ms of launch latency
+// per frame on every rank; here each is ONE single-thread kernel.  The formulas are frame_stats_kernel's (csrc/postprocess.cu) and
+// metrics_finalize + lerp (csrc/pointwise.cu, pipeline/util.py:4), the sums run over the ranks in rank order (identical on every rank).
+__global__ void band_stats_finish_kernel(const float *__restrict__ gathered, int world, const float *prev_bounds, float ma, float *bounds_out,
+                                         float *ratio_out) {
+  if (threadIdx.x != 0) return;
+  float s1 = 0.0f, s2 = 0.0f, g_lo = FLT_MAX, g_hi = -FLT_MAX, o_lo = FLT_MAX, o_hi = -FLT_MAX;
+  for (int r = 0; r < world; r++) {
+    const float *p = gathered + 6 * r;  // G1 sum, G2 sum, min / max of the sampled G1 greens, min / max of every other sampled value
+    s1 += p[0], s2 += p[1];
+    g_lo = fminf(g_lo, p[2]), g_hi = fmaxf(g_hi, p[3]), o_lo = fminf(o_lo, p[4]), o_hi = fmaxf(o_hi, p[5]);
+  }
+  const float ratio = (s1 > 0.0f && s2 > 0.0f) ? __fdiv_rn(s2, s1) : 1.0f;
+  *ratio_out = ratio;
+  float lo = o_lo, hi = o_hi;
+  if (g_lo <= g_hi) lo = fminf(lo, fmaxf(g_lo * ratio, 0.0f)), hi = fmaxf(hi, fmaxf(g_hi * ratio, 0.0f));
+  const float p0 = prev_bounds ? prev_bounds[0] : lo, p1 = prev_bounds ? prev_bounds[1] : hi;
+  bounds_out[0] = p0 + (lo - p0) * ma, bounds_out[1] = p1 + (hi - p1) * ma;
+}
+__global__ void band_metrics_finish_kernel(const float *__restrict__ sums, const float *prev_metrics, float ma, float *metrics_out) {
+  if (threadIdx.x >= 5) return;
+  const float v = sums[threadIdx.x] * (1.0f / fmaxf(sums[5], 1.0f));
+  const float p = prev_metrics ? prev_metrics[threadIdx.x] : v;
+  metrics_out[threadIdx.x] = p + (v - p) * ma;
+}
+}  // namespace
+}  // namespace tdb
+
 using namespace tdb;
 
 extern "C" {
@@ -255,6 +288,20 @@ int tdb_metrics_sliced_band(const float *rgb, int lab_input, const void *bilater
   TDB_REQUIRE(raw_sums && row_lo >= 0 && row_lo < row_hi && row_hi <= height, "metrics_sliced_band: bad arguments");
   return run_metrics_sliced(rgb, lab_input, bilateral_scratch, width, height, sigma_s, sigma_r, detail, stride, min_gray, frame_state, 1, 1,
                             nullptr, 1.0f, nullptr, row_lo, row_hi, raw_sums, stream);
+}
+
+
+int tdb_band_stats_finish(const float *gathered, int world, const float *prev_bounds, float moving_average, float *bounds_out, float *ratio_out,
+                          tdb_stream_t stream) {
+  TDB_REQUIRE(gathered && bounds_out && ratio_out && world > 0, "band_stats_finish: bad arguments");
+  band_stats_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(gathered, world, prev_bounds, moving_average, bounds_out, ratio_out);
+  return check_launch("band_stats_finish");
+}
+
+int tdb_band_metrics_finish(const float *sums, const float *prev_metrics, float moving_average, float *metrics_out, tdb_stream_t stream) {
+  TDB_REQUIRE(sums && metrics_out, "band_metrics_finish: null pointer");
+  band_metrics_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(sums, prev_metrics, moving_average, metrics_out);
+  return check_launch("band_metrics_finish");
 }
 
 }  // extern "C"

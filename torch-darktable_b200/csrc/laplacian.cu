@@ -102,14 +102,9 @@ inline FlatZones coarser(const FlatZones &f) {
 constexpr int RT = 16;            // coarse tile edge
 constexpr int RP = 2 * RT + 3;    // fine patch edge (35)
 constexpr int RPS = 24;           // row stride of a parity plane: 18 words used; 2 * 24 = 16 (mod 32) keeps the two half-warps apart
-__global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant__ ReduceBatch b, int cw, int ch, int fw, int fh,
-                                                          const FlatZones fz) {
-  __shared__ float pe[RP * RPS], po[RP * RPS];  // even / odd patch columns
-  __shared__ __half res[RT][RT];
-  const int k = blockIdx.z;
-  const __half *__restrict__ fine = b.fine[k];
-  __half *__restrict__ coarse = b.coarse[k];
-  const int cx0 = blockIdx.x * RT, cy0 = blockIdx.y * RT;
+// one 16 x 16 coarse tile at (cx0, cy0); pe / po: RP * RPS floats each (even / odd patch columns), res: RT * RT halves
+__device__ __forceinline__ void reduce_tile16(const __half *__restrict__ fine, __half *__restrict__ coarse, int cx0, int cy0, int cw, int ch,
+                                              int fw, int fh, const FlatZones &fz, float *pe, float *po, __half (*res)[RT]) {
   // coarse pixel c reads fine 2*c'-2 .. 2*c'+2 with c' clamped to [1, size-2]; patch origin = 2*cx0 - 2 covers every
   // unclamped pixel of the tile, clamped border pixels are handled by reading through the same patch when possible
   const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
@@ -186,6 +181,70 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant_
       }
   }
   coarse[(int64_t)y * cw + x] = f2h(acc);
+}
+
+// Levels >= 2, all seven pyramids (blockIdx.z), 32 x 32 coarse tiles.  A tile whose 67 x 67 fine patch lies inside the plane and is not
+// flat takes the separable path of reduce1_interior (same argument: fp16 data times k / 256 weights sum exactly in fp32, so the order
+// of the additions cannot change the result): a thread owns one coarse column and four coarse rows, 18.75 multiply-adds and 13.75
+// loads per coarse pixel instead of 50 and 25, no per-pixel clamp tests.  Everything else -- plane borders (clamped coarse
+// coordinates, reference laplacian.cu:178-208) and flat zones of the replicate padding -- goes through reduce_tile16, one 16 x 16
+// quarter at a time.
+constexpr int R2 = 32, P2 = 2 * R2 + 3, P2S = 68;  // coarse tile, fine patch 67 x 67, row stride: 34 even + 33 odd words + 1
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const __grid_constant__ ReduceBatch b, int cw, int ch, int fw, int fh,
+                                                          const FlatZones fz) {
+  __shared__ __align__(16) float sm2[P2 * P2S];
+  const int k = blockIdx.z;
+  const __half *__restrict__ fine = b.fine[k];
+  __half *__restrict__ coarse = b.coarse[k];
+  const int cx0 = blockIdx.x * R2, cy0 = blockIdx.y * R2;
+  const int fx0 = 2 * cx0 - 2, fy0 = 2 * cy0 - 2;
+  const bool inside = fx0 >= 0 && fy0 >= 0 && fx0 + P2 <= fw && fy0 + P2 <= fh && cx0 >= 1 && cy0 >= 1 && cx0 + R2 <= cw - 1 && cy0 + R2 <= ch - 1;
+  const bool flat = (fx0 + P2 - 1 <= fz.x_lo || fx0 >= fz.x_hi) || (fy0 + P2 - 1 <= fz.y_lo || fy0 >= fz.y_hi);
+  if (inside && !flat) {
+    constexpr int NPAIR = (P2 + 1) / 2;  // 34 column pairs: even column -> word kx, odd column -> word 34 + kx
+    const __half *src = fine + (int64_t)fy0 * fw + fx0;  // fx0 is even: pairs are 4-byte aligned when fw is even
+    const bool pair_loads = (fw & 1) == 0 && (reinterpret_cast<uintptr_t>(fine) & 3) == 0;
+    for (int i = threadIdx.x; i < P2 * NPAIR; i += kThreads) {
+      const int ly = i / NPAIR, kx = i - ly * NPAIR;
+      const __half *row = src + (int64_t)ly * fw + 2 * kx;
+      float ve, vo = 0.0f;
+      if (kx < NPAIR - 1) {
+        if (pair_loads) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2 *>(row));
+          ve = v.x, vo = v.y;
+        } else {
+          ve = h2f(row[0]), vo = h2f(row[1]);
+        }
+      } else {
+        ve = h2f(row[0]);  // the patch has 67 columns: the last pair has no odd member
+      }
+      sm2[ly * P2S + kx] = ve;
+      if (kx < NPAIR - 1) sm2[ly * P2S + 34 + kx] = vo;
+    }
+    __syncthreads();
+    const float w0 = 1.0f / 16.0f, w1 = 4.0f / 16.0f, w2 = 6.0f / 16.0f;
+    const int lx = threadIdx.x & 31, rg = threadIdx.x >> 5;  // coarse column, group of four coarse rows
+    const float *e = sm2 + (8 * rg) * P2S + lx;
+    float h[11];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+      const float *q = e + r * P2S;
+      h[r] = fmaf(q[2], w0, fmaf(q[35], w1, fmaf(q[1], w2, fmaf(q[34], w1, q[0] * w0))));
+    }
+    __half *o = coarse + (int64_t)(cy0 + 4 * rg) * cw + cx0 + lx;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      o[(int64_t)r * cw] = f2h(fmaf(h[2 * r + 4], w0, fmaf(h[2 * r + 3], w1, fmaf(h[2 * r + 2], w2, fmaf(h[2 * r + 1], w1, h[2 * r] * w0)))));
+    return;
+  }
+  float *pe = sm2, *po = sm2 + RP * RPS;
+  __half(*res)[RT] = reinterpret_cast<__half(*)[RT]>(sm2 + 2 * RP * RPS);
+  static_assert(2 * RP * RPS + RT * RT / 2 <= P2 * P2S, "the 16 x 16 path lives inside the 32 x 32 path's shared memory");
+  for (int q = 0; q < 4; q++) {
+    const int qx = cx0 + (q & 1) * RT, qy = cy0 + (q >> 1) * RT;
+    __syncthreads();  // the previous quarter's readers are done
+    if (qx < cw && qy < ch) reduce_tile16(fine, coarse, qx, qy, cw, ch, fw, fh, fz, pe, po, res);
+  }
 }
 
 // Level 1 of all seven pyramids straight from the fp32 image: replicate padding (laplacian.cu:90-109), the fp16 rounding of the
@@ -361,7 +420,7 @@ __device__ __forceinline__ float expand_gaussian(const __half *__restrict__ coar
     for (int j = -1; j <= 1; j++) {
       if ((xo && i < 0) || (yo && j < 0)) continue;
       const int wi = xo ? (2 * i + 1) : (2 * i + 2), wj = yo ? (2 * j + 1) : (2 * j + 2);
-      c += h2f(coarse[(int64_t)(cy + j) * cw + (cx + i)]) * w[wi] * w[wj];
+      c = fmaf(h2f(coarse[(int64_t)(cy + j) * cw + (cx + i)]), w[wi] * w[wj], c);  // exact products: see expand_from
     }
   return 4.0f * c;
 }
@@ -445,7 +504,9 @@ __device__ __forceinline__ float expand_from(const Taps9 &t) {  // expand_gaussi
     for (int j = -1; j <= 1; j++) {
       if ((XO && i < 0) || (YO && j < 0)) continue;
       const int wi = XO ? (2 * i + 1) : (2 * i + 2), wj = YO ? (2 * j + 1) : (2 * j + 2);
-      c += t.v[j + 1][i + 1] * w[wi] * w[wj];
+      // (v * w_i) * w_j of the reference as ONE multiply-add: v is an fp16 value and w_i * w_j = k / 256, so both products are exact
+      // in fp32 and the two forms round identically; the compiler cannot know that and would keep two multiplies per tap
+      c = fmaf(t.v[j + 1][i + 1], w[wi] * w[wj], c);
     }
   return 4.0f * c;
 }
@@ -556,7 +617,7 @@ int tdb_laplacian(const float *lum, float *out, void *scratch, int width, int he
     ReduceBatch b{};
     for (int k = 0; k < G; k++) b.fine[k] = base + p.proc[k][l - 1], b.coarse[k] = base + p.proc[k][l];
     b.fine[G] = input_level(l - 1), b.coarse[G] = input_level(l);
-    reduce_kernel<<<dim3(div_up(p.w[l], RT), div_up(p.h[l], RT), NP), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], fz);
+    reduce_kernel<<<dim3(div_up(p.w[l], R2), div_up(p.h[l], R2), NP), kThreads, 0, s>>>(b, p.w[l], p.h[l], p.w[l - 1], p.h[l - 1], fz);
     if (int e = check_launch("laplacian_reduce")) return e;
   }
   // regions of each level that can reach the cropped output: level l needs level l+1 on region/2 -+ 1

@@ -395,7 +395,7 @@ __device__ __forceinline__ void rcd_tile(float *sm, const CfaSource &src_in, flo
 
 __global__ void __launch_bounds__(kThreads256) rcd_kernel(CfaSource src, float *__restrict__ rgb, int width, int height, uint32_t filters,
                                                        TileRects rects) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
   rcd_tile<kThreads256>(sm, src, rgb, width, height, filters, rects, blockIdx.x, blockIdx.x, blockIdx.y);
 }
 
@@ -409,7 +409,7 @@ template <bool kG0>
 __global__ void __launch_bounds__(v3::kThreads3, 2) rcd3_kernel(CfaSource src, float *__restrict__ rgb, int width, int height,
                                                                 uint32_t filters, int x_origin, int by_lo, int nbx, int n_interior,
                                                                 TileRects rects) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
   const int b = blockIdx.x;
   if (b < n_interior) v3::rcd3_tile<kG0>(sm, src, rgb, width, height, filters, x_origin, by_lo, b % nbx, b / nbx);
   else rcd_tile<kThreads256>(sm, src, rgb, width, height, filters, rects, b - n_interior, 0, 0);
@@ -429,19 +429,6 @@ __global__ void __launch_bounds__(v4::NT, 3) rcd_strip_kernel(const __grid_const
   }
   if (a.frame_first) b -= a.n_frame;
   v4::rcd_strip<kG0>(sm, &tmap, a, b);
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point query: libtdb200 does not link libcuda
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled() {
-  static const EncodeTiledFn fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
 }
 
 int env_int(const char *name, int fallback) {
@@ -476,20 +463,9 @@ int launch_rcd(const CfaSource &src, float *rgb, int width, int height, uint32_t
   static const int use_strips = env_int("TDB_RCD_STRIPS", 1);
   const int y_end = (height - 16) / 32 * 32;
   const bool strip_align = src.cfa ? true : reinterpret_cast<uintptr_t>(src.packed) % 16 == 0;
-  if (use_strips && aligned && strip_align && nbx >= 1 && y_end >= 64 && (!src.cfa || encode_tiled())) {
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof tmap);
-    if (src.cfa) {
-      const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)height}, strides[1] = {(cuuint64_t)width * sizeof(float)};
-      const cuuint32_t box[2] = {(cuuint32_t)v4::PW, (cuuint32_t)v4::R}, estr[2] = {1, 1};
-      const CUresult r = encode_tiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(src.cfa), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
-        set_error("RCD: cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return TDB_ECUDA;
-      }
-    }
+  CUtensorMap tmap;
+  const bool have_map = make_tensor_map_f32(&tmap, src.cfa, width, height, v4::PW, v4::R);  // zeroed (and unused) for a packed source
+  if (use_strips && aligned && strip_align && nbx >= 1 && y_end >= 64 && (!src.cfa || have_map)) {
     v4::StripArgs a{};
     a.src = src, a.rgb = rgb, a.width = width, a.height = height, a.filters = filters, a.x_origin = x_origin;
     a.nstrips = nbx, a.y_start = 32, a.n_iter = (y_end - 32) / v4::R;

@@ -32,8 +32,6 @@
 // 20 quads = one 2 x 4 block per thread and step), three CTAs per SM.
 #pragma once
 
-#include <cuda.h>
-
 #include "rcd_planar.cuh"
 
 namespace tdb {
@@ -87,12 +85,6 @@ struct StripArgs {
   int frame_first;       // the 32 x 32 frame tiles occupy the first blocks of the grid instead of the last
   int n_frame;
 };
-
-__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(dst_smem)),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(bar))
-               : "memory");
-}
 
 // rows [16, 16 + kRows) of a plane -> rows [0, kRows): the part of its window that the next iteration still reads
 template <int kRows, int kStride>

@@ -1,6 +1,7 @@
 // Shared host/device helpers of libtdb200 (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -40,6 +41,10 @@ class DeviceOnce {
   std::mutex mutex_;
 };
 void count_launches(int n);
+// Tensor map of a row-major float32 (height, width) plane for boxes of box_w x box_h elements (cuTensorMapEncodeTiled, reached through
+// the runtime's driver entry point query: libtdb200 does not link libcuda).  Needs a 16-byte aligned base and width % 4 == 0; returns
+// false when the plane does not qualify or the driver call is unavailable -- callers then stage with ordinary loads.
+bool make_tensor_map_f32(CUtensorMap *map, const float *plane, int width, int height, int box_w, int box_h);
 // a per-device side stream ordered after everything already queued on `main` (returns `main` itself when unavailable)
 cudaStream_t fork_side(cudaStream_t main);
 void join_side(cudaStream_t main, cudaStream_t side);
@@ -133,6 +138,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// 2-D tensor-map load (cp.async.bulk.tensor.2d, SASS UTMALDG): the box whose first element has coordinates (c0, c1) = (column, row)
+// lands densely in shared memory (row pitch = box width; destination 128-byte aligned); elements outside the tensor arrive as zeros,
+// which is what the zero-filled halos of the reference's demosaic kernels hold (csrc/debayer/ppg.cu:61,159,270)
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_addr(bar))
                : "memory");
 }
 // shared -> global: the writers of the shared-memory tile call bulk_store_fence() before the barrier that precedes the copy

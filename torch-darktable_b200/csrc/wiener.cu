@@ -482,7 +482,9 @@ struct Args {
   fft::cpx tw[32];      // fft_quad twiddles
 };
 
-__global__ void __launch_bounds__(kThreads, 2) wiener32_shared_kernel(const Args a) {
+// kCtas: resident CTAs per SM the register allocation is sized for (2: 127 registers; 3: 80 registers, 16 bytes of spills -- 24 warps per SM)
+template <int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) wiener32_shared_kernel(const Args a) {
   extern __shared__ float2 s_shr[];
   float2 *spec = s_shr, *accu = s_shr + BUFC * LD, *csum = accu + BUFC * LD, *twt = csum + BUFC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -789,10 +791,16 @@ int run_tiles_shared(const float *in, float *acc, int width, int height, int cha
   memcpy(a.what, tables.what, sizeof a.what), memcpy(a.tw, tables.tw, sizeof a.tw);
   static DeviceOnce attr;
   attr.run([&] {
-    cudaFuncSetAttribute(shr::wiener32_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
+    cudaFuncSetAttribute(shr::wiener32_shared_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
+    cudaFuncSetAttribute(shr::wiener32_shared_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
   });
-  const int grid = a.total_steps < 2 * kNumSMs ? a.total_steps : 2 * kNumSMs;
-  shr::wiener32_shared_kernel<<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  static const int ctas = [] {
+    const char *e = getenv("TDB_WIENER_CTAS");
+    return e && atoi(e) == 3 ? 3 : 2;  // measured at 4K: 0.2165 ms with two CTAs per SM, 0.2221 ms with three (the kernel is not latency-bound)
+  }();
+  const int grid = a.total_steps < ctas * kNumSMs ? a.total_steps : ctas * kNumSMs;
+  if (ctas == 3) shr::wiener32_shared_kernel<3><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  else shr::wiener32_shared_kernel<2><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   return check_launch("wiener_tiles");
 }
 

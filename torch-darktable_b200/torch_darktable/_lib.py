@@ -75,6 +75,8 @@ _SIGNATURES = {
   'tdb_bilateral_slice_tonemap': (_I, [_P, _I, _P, _P, _I, _I, _F, _F, _F, _I, _P, _F, _F, _F, _F, _P, _I, _P]),
   'tdb_postprocess_deferred_band': (_I, [_P, _P, _P, _I, _I, _U32, _I, _I, _I, _I, _P, _P]),
   'tdb_metrics_sliced_band': (_I, [_P, _I, _P, _I, _I, _F, _F, _F, _I, _F, _P, _I, _I, _P, _P]),
+  'tdb_band_stats_finish': (_I, [_P, _I, _P, _F, _P, _P, _P]),
+  'tdb_band_metrics_finish': (_I, [_P, _P, _F, _P, _P]),
   'tdb_bilateral_grid_rgb': (_I, [_P, _P, _I, _I, _F, _F, _P]),
   'tdb_channel_noise_scratch_bytes': (_SZ, [_I, _I, _I]),
   'tdb_channel_noise': (_I, [_P, _I, _I, _I, _P, _P, _P]),

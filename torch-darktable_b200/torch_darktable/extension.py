@@ -885,6 +885,23 @@ class FramePipeline:
     return out
 
 
+def band_stats_finish(gathered: torch.Tensor, prev_bounds: torch.Tensor | None, moving_average: float, bounds_out: torch.Tensor):
+  """(world, 6) gathered band statistics -> green ratio (returned) and the EMA of the bounds (written into bounds_out, which may be
+  prev_bounds itself); one kernel (csrc/fused.cu)."""
+  _cuda_f32(gathered, 'gathered')
+  g = gathered.contiguous()
+  ratio = torch.empty(1, dtype=torch.float32, device=g.device)
+  with torch.cuda.device(g.device):
+    check(lib.tdb_band_stats_finish(_ptr(g), g.size(0), _ptr(prev_bounds), float(moving_average), _ptr(bounds_out), _ptr(ratio), _stream(g.device)))
+  return ratio
+
+
+def band_metrics_finish(sums: torch.Tensor, prev_metrics: torch.Tensor | None, moving_average: float, metrics_out: torch.Tensor):
+  _cuda_f32(sums, 'sums')
+  with torch.cuda.device(sums.device):
+    check(lib.tdb_band_metrics_finish(_ptr(sums.contiguous()), _ptr(prev_metrics), float(moving_average), _ptr(metrics_out), _stream(sums.device)))
+
+
 def launch_count() -> int:
   """Kernels launched through libtdb200 by this process so far."""
   return _lib.launch_count()
@@ -907,7 +924,7 @@ extension = SimpleNamespace(
   # fused additions (not in the reference binding)
   unpack12_wb=unpack12_wb, demosaic_packed=demosaic_packed, normalize=normalize, lerp=lerp, tonemap=tonemap,
   FramePipeline=FramePipeline, image_metric_sums=image_metric_sums, metrics_from_sums=metrics_from_sums, green_sums=green_sums, green_eq_apply=green_eq_apply,
-  launch_count=launch_count, channel_noise=channel_noise,
+  launch_count=launch_count, channel_noise=channel_noise, band_stats_finish=band_stats_finish, band_metrics_finish=band_metrics_finish,
 )
 
 __all__ = ['extension']

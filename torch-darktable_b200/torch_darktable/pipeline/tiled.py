@@ -313,17 +313,12 @@ class TiledFrameProcessor:
     smoothed, raw = frame.smooth_band(post, rgb, lo, hi)
     self._mark('demosaic + smoothing')
     stats = col.all_gather(raw)  # (world, 6): one collective for the green sums, the minima and the maxima
-    sums = stats[:, 0:2].sum(0)
-    mins, maxs = stats[:, [2, 4]].min(0).values, stats[:, [3, 5]].max(0).values
-    one = torch.ones_like(sums[0])
-    ratio = torch.where((sums[0] > 0) & (sums[1] > 0), sums[1] / sums[0], one).reshape(1)
-    # bounds of the equilibrated image: the G1 greens take the ratio (x -> max(0, x * ratio) is monotone), csrc/postprocess.cu
-    have_g1 = mins[0] <= maxs[0]
-    zero = torch.zeros_like(one)
-    lo_v = torch.where(have_g1, torch.minimum(mins[1], torch.maximum(mins[0] * ratio[0], zero)), mins[1])
-    hi_v = torch.where(have_g1, torch.maximum(maxs[1], torch.maximum(maxs[0] * ratio[0], zero)), maxs[1])
-    bounds = torch.stack([lo_v, hi_v])
-    self.bounds = lerp(self.bounds if self.bounds is not None else bounds, bounds, s.moving_average)
+    # ratio, bounds of the equilibrated image (the G1 greens take the ratio: x -> max(0, x * ratio) is monotone) and their EMA: one kernel,
+    # the state is updated in place
+    prev = self.bounds
+    if self.bounds is None:
+      self.bounds = torch.empty(2, dtype=torch.float32, device=self.device)
+    ratio = extension.band_stats_finish(stats, prev, s.moving_average, self.bounds)
     self._mark('all-gather of the band statistics + bounds')
 
     image = frame.prepare(smoothed, ratio, self.bounds, wiener)
@@ -335,8 +330,10 @@ class TiledFrameProcessor:
     local_sums = frame.metric_sums_band(image, bil, s.bilateral, lo, hi, lab_input=lab)
     self._mark('prepare + Wiener + bilateral grid + metric sums')
     msums = col.all_reduce(local_sums, 'sum')
-    metrics = extension.metrics_from_sums(msums)
-    self.metrics = lerp(self.metrics if self.metrics is not None else metrics, metrics, s.moving_average)
+    prev = self.metrics
+    if self.metrics is None:
+      self.metrics = torch.empty(5, dtype=torch.float32, device=self.device)
+    extension.band_metrics_finish(msums, prev, s.moving_average, self.metrics)
     self._mark('all-reduce of the metric sums + metrics')
 
     params = self.td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
