@@ -7,7 +7,8 @@ One "step" = one pass of the hot path over the rank's batch of 32 synthetic 12-b
 (RCD demosaic + post-process + Wiener log-luminance denoise + bilateral local contrast + adaptive ACES, rotate_270:
 the `artichoke` camera settings).  Prints ONE JSON line on rank 0.
 
-  value      frames already resident in HBM, CUDA-event time, max over ranks
+  value      frames already resident in HBM, CUDA-event time, max over ranks; the step is ONE call of ImageProcessor.process_batch, i.e. one
+             CUDA-graph replay of its 9 x 32 kernels (--no-graph: 32 per-frame process() calls, 1.6 % slower at 4K)
   e2e        the same through pinned HOST buffers (H2D of every packed frame and D2H of every uint8 result inside the
              timed region), via torch_darktable.pipeline.batch.HostFrameRunner; `copy_ceiling` = the same bytes copied with
              no kernel running, all ranks at once, measured in the same run; `frac_of_ceiling` = e2e / that ceiling
@@ -368,17 +369,30 @@ def run_ours(args):
   proc = ImageProcessor((WIDTH, HEIGHT), td.BayerPattern.RGGB, td.PackedFormat.Packed12, settings, dev, None, ImageTransform.rotate_270)
   px_step = WIDTH * HEIGHT * FRAMES
   last = [None]
+  use_graph = not args.no_graph
+  batch_in = [torch.stack(resident)]  # (FRAMES, bytes); replaced by the graph's own input buffer after the capturing call
 
-  def step_resident():
+  def step_frames():  # frame by frame through ImageProcessor.process (the per-kernel timing pass, and the step itself with --no-graph)
     for i, f in enumerate(resident):
       out = proc.process(f, 'cam')
       if i == 0:
-        last[0] = out  # frame 0 (scene seed 1234) of the latest step: compared with the oracle below
+        last[0] = out
 
+  def step_resident():
+    # one call of the batch entry: every frame its own image set, exactly FRAMES calls of ImageProcessor.process; after the first call
+    # (which runs eagerly and captures) the whole step is ONE CUDA-graph replay of the 9 x FRAMES kernels
+    if not use_graph:
+      return step_frames()
+    last[0] = proc.process_batch(batch_in[0], 'cam', graph=True)[0]
+
+  launches0 = _lib.launch_count()
+  step_resident()  # with the graph: eager pass + capture pass, each issuing the step's launches once
+  per_step_launches = (_lib.launch_count() - launches0) // (2 if use_graph else 1)
+  if use_graph:
+    batch_in[0] = proc.batch_input_buffer(FRAMES)  # already holds the frames: later steps skip the device-to-device copy
   with ClockSampler(local_rank) as clocks:
-    launches0 = _lib.launch_count()
     ms = timed_steps(torch, dist, step_resident, args.steps, args.warmup, world)
-    launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup) * args.steps
+  launches = per_step_launches * args.steps  # kernels of the timed region (graph nodes are launches too; the library counter only sees eager ones)
   timed_out0 = last[0].clone()
   clock_summary = clocks.summary()
 
@@ -386,7 +400,7 @@ def run_ours(args):
   stream = torch.cuda.current_stream(dev)
   torch.cuda.synchronize()
   _lib.timing_begin(stream.cuda_stream)
-  step_resident()
+  step_frames()
   table = _lib.timing_end()
   peak, peak_src = measured_peak_gbs()
   pipe = measure_pipe_peaks(torch, _lib, dev)
@@ -402,8 +416,10 @@ def run_ours(args):
   def step_e2e():  # batches are streamed: the copy-in of the next step overlaps the tail of this one, one host wait at the end
     runner.run(host, host_out, after_caller=False)
 
+  allocs0 = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
   e2e_ms = timed_steps(torch, dist, step_e2e, args.steps, max(args.warmup, 1), world)
   runner.wait()
+  e2e_device_allocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - allocs0  # cudaMalloc calls (they synchronise): should be 0 after warm-up
 
   # the same bytes with no kernel running, both directions at once, all ranks at once: the ceiling of the e2e figure on this box
   s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -441,11 +457,13 @@ def run_ours(args):
       'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(),
       'e2e': {'value': round(e2e_value, 1), 'unit': 'MP/s', 'ms_per_step': round(e2e_ms, 3),
               'h2d_bytes_per_step': FRAMES * WIDTH * HEIGHT * 3 // 2, 'd2h_bytes_per_step': FRAMES * WIDTH * HEIGHT * 3,
-              'copy_ceiling': round(ceiling, 1), 'copy_ceiling_ms_per_step': round(copy_ms, 3), 'frac_of_ceiling': round(e2e_value / ceiling, 4),
+              'device_allocs_incl_warmup': int(e2e_device_allocs), 'copy_ceiling': round(ceiling, 1), 'copy_ceiling_ms_per_step': round(copy_ms, 3), 'frac_of_ceiling': round(e2e_value / ceiling, 4),
               'copy_ceiling_gbs_per_gpu': round(FRAMES * WIDTH * HEIGHT * 4.5 / 1e6 / copy_ms, 1)},
-      'e2e_method': 'HostFrameRunner: three streams (H2D / kernels / D2H) over three device slots, pinned host buffers, steps streamed into '
-                    'each other, one host wait inside the closing synchronise; host thread + pinned pages bound to the GPU\'s NUMA node',
+      'e2e_method': 'HostFrameRunner: copy-in stream / two compute lanes (ImageProcessor.submit: two frames in flight) / copy-out stream over '
+                    'three device slots, pinned host buffers, steps streamed into each other, one host wait inside the closing synchronise; '
+                    'host thread + pinned pages bound to the GPU\'s NUMA node where the platform exposes one',
       'host_binding': binding,
+      'resident_method': ('ImageProcessor.process_batch: one CUDA-graph replay per step' if use_graph else 'ImageProcessor.process per frame'),
       'gpu_launches': int(launches), 'roofline': roofline, 'pipe_peaks_measured': pipe, 'stages': stages, 'clocks': clock_summary,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -534,6 +552,7 @@ def main():
   ap.add_argument('--frames', type=int, default=FRAMES, help='frames per GPU per step (32 = the headline config; smaller only for profiling)')
   ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle leg (profiling runs)')
   ap.add_argument('--no-extra', action='store_true', help='skip the configs[4] legs (profiling runs)')
+  ap.add_argument('--no-graph', action='store_true', help='resident leg through per-frame process() calls instead of the CUDA-graph batch entry')
   ap.add_argument('--no-bind', action='store_true', help='do not bind the host thread to the GPU\'s NUMA node (A/B of the e2e leg)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)

@@ -105,3 +105,48 @@ def test_state_from_stage_path_carries_into_the_fused_path(td):
   d = (ra.to(torch.int16) - rb.to(torch.int16)).abs()
   assert int(d.max()) <= 1 and float((d > 0).float().mean()) <= 1e-3
   assert torch.allclose(a.bounds, b.bounds, atol=2e-6) and torch.allclose(a.metrics, b.metrics, atol=2e-5)
+
+
+@pytest.mark.parametrize('ma', [1.0, 0.3])
+def test_submit_two_frames_in_flight_equals_sequential_process(td, ma):
+  """`submit` overlaps consecutive frames on two lanes; the EMA chain must stay that of sequential `process` calls, also when eager
+  calls are interleaved (they join the lanes and take the state over) and when the caller's tensors are short-lived."""
+  import torch
+  h, w = 250, 372
+  fr = frames_of(h, w, range(30, 39))
+  seq = make_processor(td, w, h, ma, 'none')
+  want = [seq.process(f, 'cam') for f in fr]
+  ovl = make_processor(td, w, h, ma, 'none')
+  got = []
+  for i, f in enumerate(fr):
+    if i == 4:  # an eager call in the middle
+      got.append(ovl.process(f.clone(), 'cam'))
+    else:
+      res, done = ovl.submit(f.clone(), 'cam')  # the clone dies right after the call: the lane must still read valid bytes
+      got.append(res)
+  ovl.join()
+  torch.cuda.synchronize()
+  for i, (g, wv) in enumerate(zip(got, want)):
+    assert_same(g, wv, f'frame {i}: submit vs process')
+  assert torch.allclose(ovl.bounds, seq.bounds, atol=1e-6) and torch.allclose(ovl.metrics, seq.metrics, atol=1e-6)
+  assert ovl.bounds is ovl._bounds_pp[0]  # join() leaves the state in its resting buffers
+
+
+def test_host_frame_runner_matches_process(td):
+  """The three-stream host runner (pinned in / out, two frames in flight on the lanes) against per-frame process calls."""
+  import torch
+  from torch_darktable.pipeline.batch import HostFrameRunner
+  h, w = 250, 372
+  fr = frames_of(h, w, range(50, 57))
+  ref = make_processor(td, w, h, 0.5, 'rotate_270')
+  want = [ref.process(f, 'cam').cpu() for f in fr]
+  proc = make_processor(td, w, h, 0.5, 'rotate_270')
+  runner = HostFrameRunner(proc)
+  host_in = [f.cpu().pin_memory() for f in fr]
+  host_out = [torch.empty((w, h, 3), dtype=torch.uint8).pin_memory() for _ in fr]
+  runner.run(host_in[:4], host_out[:4])
+  runner.run(host_in[4:], host_out[4:], after_caller=False)
+  runner.wait()
+  torch.cuda.synchronize()
+  for i, (g, wv) in enumerate(zip(host_out, want)):
+    assert_same(g.cuda(), wv.cuda(), f'frame {i}: host runner vs process')

@@ -10,7 +10,7 @@ if [ -z "$2" ]; then
 fi
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_ours_$TAG.json 2> gpurun_out/bench_ours_$TAG.err; tail -c 800 gpurun_out/bench_ours_$TAG.err
 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; tail -c 600 gpurun_out/bench_ref_$TAG.err
-CMD="python bench.py --frames 2 --steps 1 --warmup 3 --no-cpu-baseline --no-extra"
+CMD="python bench.py --frames 2 --steps 1 --warmup 3 --no-cpu-baseline --no-extra --no-graph"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \

@@ -109,10 +109,10 @@ class HostFrameRunner:
         if self._results[slot] is not None:
           self._s_compute.wait_event(self._out_done[slot])  # the copy-out of the result this slot held has finished
           self._results[slot] = None
-        result = self.processor.process(self._in[slot], name)
-        self._consumed[slot].record(self._s_compute)
+        # two frames in flight on the processor's lanes; `done` marks both "input consumed" and "result ready"
+        result, done = self.processor.submit(self._in[slot], name, track=False)  # slots and results are kept alive here until their copies are ordered
+        self._consumed[slot] = self._ready[slot] = done
         self._used[slot] = True
-        self._ready[slot].record(self._s_compute)
         self._results[slot] = result
       with torch.cuda.stream(self._s_out):
         self._s_out.wait_event(self._ready[slot])
