@@ -296,9 +296,10 @@ def leg_batch_20mp(torch, dist, td, dev, rank, world, total_frames=1024):
   scenes = [device_packed_scene(torch, td, h, w, 20 + g, dev) for g in range(4)]
   mine = range(rank, total_frames, world)  # global frame indices of this rank
 
-  def run(indices):
+  def run(indices):  # two frames in flight (ImageProcessor.submit), EMA chained frame to frame as by process()
     for i in indices:
-      proc.process(scenes[i % 4], 'cam')
+      proc.submit(scenes[i % 4], 'cam', track=False)
+    proc.join()
 
   run(list(mine)[:8])
   ms = timed_steps(torch, dist, lambda: run(mine), 1, 0, world)
