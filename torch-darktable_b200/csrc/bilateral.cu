@@ -171,13 +171,11 @@ __global__ void __launch_bounds__(kThreads) grid_build_kernel(const float *__res
     const int i = ci0 + li, j = cj0 + lj;
     float *bins = cells + lj * GPX + li;
     const bool in_grid = i >= 0 && j >= 0 && i < g.x && j < g.y;
-    for (int z = 0; z < g.z; z++) {
-      float v = 0.0f;
-      if (pile_x && in_grid) {
-        if (i == g.x - 1) v += __ldg(pile_x + j * g.z + z);
-        if (j == g.y - 1) v += __ldg(pile_y + i * g.z + z);
-      }
-      bins[z * ZS] = v;
+    if (pile_x != nullptr && in_grid && (i == g.x - 1 || j == g.y - 1)) {  // last cell column / row of a saturating grid: start from the piles
+      for (int z = 0; z < g.z; z++)
+        bins[z * ZS] = (i == g.x - 1 ? __ldg(pile_x + j * g.z + z) : 0.0f) + (j == g.y - 1 ? __ldg(pile_y + i * g.z + z) : 0.0f);
+    } else {
+      for (int z = 0; z < g.z; z++) bins[z * ZS] = 0.0f;
     }
     if (!in_grid) continue;
     if (kS2) {
