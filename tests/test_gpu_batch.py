@@ -150,3 +150,26 @@ def test_host_frame_runner_matches_process(td):
   torch.cuda.synchronize()
   for i, (g, wv) in enumerate(zip(host_out, want)):
     assert_same(g.cuda(), wv.cuda(), f'frame {i}: host runner vs process')
+
+
+@pytest.mark.parametrize('kw', [dict(postprocess=False), dict(enable_denoise=False), dict(enable_bilateral=False), dict(enable_denoise=False, enable_bilateral=False)])
+def test_batch_graph_with_other_stage_combinations(td, kw):
+  """Settings that leave the nine-launch configuration (no post-process: frames run in line; no denoise / no bilateral: shorter lanes)
+  go through the same batch entry and graph."""
+  import torch
+  from torch_darktable.pipeline import ImageProcessingSettings, ImageProcessor, ImageTransform
+  from torch_darktable.pipeline.config import Debayer, ToneMapper
+  h, w = 192, 256
+  base = dict(debayer=Debayer.ppg, tone_mapping=ToneMapper.reinhard, enable_denoise=True, enable_bilateral=True, postprocess=True,
+              tone_gamma=1.5, tone_intensity=2.0, light_adapt=0.8, vibrance=0.5, moving_average=0.5)
+  base.update(kw)
+  mk = lambda: ImageProcessor((w, h), td.BayerPattern.RGGB, td.PackedFormat.Packed12, ImageProcessingSettings(**base), torch.device('cuda:0'),  # noqa: E731
+                              (1.8, 1.0, 2.1), ImageTransform.flip_horiz)
+  batches = [frames_of(h, w, range(60 + 3 * b, 63 + 3 * b)) for b in range(3)]
+  seq, bat = mk(), mk()
+  for batch in batches:
+    want = [seq.process(f, 'cam') for f in batch]
+    got = bat.process_batch(batch, 'cam', graph=True)
+    for i in range(3):
+      assert_same(got[i], want[i], f'{kw} frame {i}')
+  assert torch.allclose(bat.bounds, seq.bounds, atol=1e-6) and torch.allclose(bat.metrics, seq.metrics, atol=1e-6)
