@@ -338,7 +338,7 @@ def leg_tiled_200mp(torch, dist, td, dev, rank, world, steps=3):
                      '(sigma 8/0.1) + adaptive ACES', 'scaling': 'strong', 'halo_rows': proc.halo if world > 1 else 0,
          'halo_bytes_per_neighbour': proc.halo * w * 3 // 2 if world > 1 else 0, 'ms_per_frame': round(ms, 3),
          'value': round(w * h / 1e6 / (ms / 1e3), 1), 'unit': 'MP/s', 'checksum_u8_sum': int(checksum.item()),
-         'collectives': 'packed halo rows by NCCL send/recv + 2 all-reduces of <= 6 floats' if world > 1 else 'none'}
+         'collectives': 'packed halo rows by NCCL send/recv; one all-gather + one all-reduce of 6 floats' if world > 1 else 'none'}
   del proc, own, out
   torch.cuda.empty_cache()
   return res
