@@ -418,8 +418,12 @@ def run_ours(args):
     runner.run(host, host_out, after_caller=False)
 
   allocs0 = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
-  e2e_ms = timed_steps(torch, dist, step_e2e, args.steps, max(args.warmup, 1), world)
-  runner.wait()
+  with ClockSampler(local_rank) as clocks_e2e:  # the end-to-end timed region is sampled too
+    e2e_ms = timed_steps(torch, dist, step_e2e, args.steps, max(args.warmup, 1), world)
+    runner.wait()
+  e2e_clocks = clocks_e2e.summary()
+  if e2e_clocks['samples']:
+    clock_summary['e2e_leg'] = {k: e2e_clocks[k] for k in ('sm_mhz', 'reasons', 'samples')}
   e2e_device_allocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - allocs0  # cudaMalloc calls (they synchronise): should be 0 after warm-up
 
   # the same bytes with no kernel running, both directions at once, all ranks at once: the ceiling of the e2e figure on this box

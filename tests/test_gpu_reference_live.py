@@ -76,6 +76,8 @@ def run_reference(tmp_path: Path, jobs: list[dict]) -> dict:
   for job in jobs:
     outs[job['name']] = {p.name[len(job['name']) + 1:-4]: np.load(p) for p in tmp_path.glob(f"{job['name']}.*.npy")
                          if '.in.' not in p.name}
+  for p in tmp_path.glob('*.npy'):  # up to 600 MB per array: do not let a session pile them up under /tmp
+    p.unlink()
   return outs
 
 
