@@ -43,6 +43,11 @@ int tdb_version(void);
 const char *tdb_last_error(void);
 /* number of kernel launches issued through this library by the calling process (for bench.py's gpu_launches) */
 uint64_t tdb_launch_count(void);
+/* Hint for the CALLING THREAD: the launches that follow belong to `lanes` frames that are in flight on different streams at the same
+ * time (0 or 1: one stream at a time, the default).  Kernels whose register allocation would otherwise fill an SM on their own then
+ * launch a variant that leaves room for another kernel's CTA (the Wiener tile kernel: 104 instead of 128 registers -- 5 % slower alone,
+ * 1.3 % faster frames when two are in flight).  Results do not depend on it. */
+void tdb_set_concurrency_hint(int lanes);
 /* Optional per-kernel timing (the counterpart of the reference's CudaTimer, csrc/cuda_utils.h:40-85).  Between
  * tdb_timing_begin and tdb_timing_end every launch of the calling thread is followed by a cudaEventRecord on its
  * stream; tdb_timing_end synchronises and writes "kernel_name,launches,total_ms" lines into buf (returns the number of

@@ -84,6 +84,9 @@ void join_side(cudaStream_t main, cudaStream_t side) {
 
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static thread_local int g_concurrent_lanes = 0;
+int concurrent_lanes() { return g_concurrent_lanes; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 bool make_tensor_map_f32(CUtensorMap *map, const float *plane, int width, int height, int box_w, int box_h) {
@@ -116,6 +119,7 @@ int check_launch(const char *what) {
 
 extern "C" {
 int tdb_version(void) { return 100; }
+void tdb_set_concurrency_hint(int lanes) { tdb::g_concurrent_lanes = lanes > 0 ? lanes : 0; }
 const char *tdb_last_error(void) { return tdb::g_error; }
 uint64_t tdb_launch_count(void) { return tdb::g_launches.load(std::memory_order_relaxed); }
 

@@ -41,6 +41,8 @@ class DeviceOnce {
   std::mutex mutex_;
 };
 void count_launches(int n);
+// > 1 while the calling thread issues work for several frames in flight on different streams (tdb_set_concurrency_hint)
+int concurrent_lanes();
 // Tensor map of a row-major float32 (height, width) plane for boxes of box_w x box_h elements (cuTensorMapEncodeTiled, reached through
 // the runtime's driver entry point query: libtdb200 does not link libcuda).  Needs a 16-byte aligned base and width % 4 == 0; returns
 // false when the plane does not qualify or the driver call is unavailable -- callers then stage with ordinary loads.

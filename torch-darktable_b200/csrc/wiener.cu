@@ -483,8 +483,7 @@ struct Args {
 };
 
 // kCtas: resident CTAs per SM the register allocation is sized for (2: 127 registers; 3: 80 registers, 16 bytes of spills -- 24 warps per SM)
-template <int kCtas>
-__global__ void __launch_bounds__(kThreads, kCtas) wiener32_shared_kernel(const Args a) {
+__device__ __forceinline__ void wiener32_shared_body(const Args &a) {
   extern __shared__ float2 s_shr[];
   float2 *spec = s_shr, *accu = s_shr + BUFC * LD, *csum = accu + BUFC * LD, *twt = csum + BUFC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -676,6 +675,13 @@ __global__ void __launch_bounds__(kThreads, kCtas) wiener32_shared_kernel(const 
   }
 }
 
+template <int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) wiener32_shared_kernel(const Args a) { wiener32_shared_body(a); }
+// The same body capped at kRegs registers per thread without a residency promise: two CTAs of it leave a quarter of the SM's
+// register file to a CTA of ANOTHER kernel, which matters when two frames are in flight (ImageProcessor.submit)
+template <int kRegs>
+__global__ void __maxnreg__(kRegs) wiener32_shared_kernel_capped(const Args a) { wiener32_shared_body(a); }
+
 }  // namespace shr
 
 // closed-form weight mask: sum over the overlap^2 covering tiles of (w_fft * w_interp)(x) * (w_fft * w_interp)(y)
@@ -793,13 +799,24 @@ int run_tiles_shared(const float *in, float *acc, int width, int height, int cha
   attr.run([&] {
     cudaFuncSetAttribute(shr::wiener32_shared_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
     cudaFuncSetAttribute(shr::wiener32_shared_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
+    cudaFuncSetAttribute(shr::wiener32_shared_kernel_capped<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
+    cudaFuncSetAttribute(shr::wiener32_shared_kernel_capped<104>, cudaFuncAttributeMaxDynamicSharedMemorySize, shr::kSmemBytes);
   });
   static const int ctas = [] {
     const char *e = getenv("TDB_WIENER_CTAS");
     return e && atoi(e) == 3 ? 3 : 2;  // measured at 4K: 0.2165 ms with two CTAs per SM, 0.2221 ms with three (the kernel is not latency-bound)
   }();
+  // with another frame in flight on a second stream (tdb_set_concurrency_hint) the 104-register variant lets other kernels' CTAs
+  // share the SM: measured at 4K with two lanes 10.50 -> 10.63 GP/s, although the kernel alone runs 0.219 -> 0.231 ms
+  static const int forced_regs = [] {
+    const char *e = getenv("TDB_WIENER_REGS");
+    return e ? atoi(e) : -1;
+  }();
+  const int regs = forced_regs >= 0 ? forced_regs : (concurrent_lanes() > 1 ? 104 : 0);
   const int grid = a.total_steps < ctas * kNumSMs ? a.total_steps : ctas * kNumSMs;
-  if (ctas == 3) shr::wiener32_shared_kernel<3><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  if (regs == 96) shr::wiener32_shared_kernel_capped<96><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  else if (regs == 104) shr::wiener32_shared_kernel_capped<104><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
+  else if (ctas == 3) shr::wiener32_shared_kernel<3><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   else shr::wiener32_shared_kernel<2><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   return check_launch("wiener_tiles");
 }

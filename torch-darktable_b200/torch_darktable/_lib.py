@@ -26,6 +26,7 @@ _SIGNATURES = {
   'tdb_version': (_I, []),
   'tdb_last_error': (C.c_char_p, []),
   'tdb_launch_count': (C.c_uint64, []),
+  'tdb_set_concurrency_hint': (None, [_I]),
   'tdb_timing_begin': (None, [_P]),
   'tdb_timing_end': (_SZ, [C.c_char_p, _SZ]),
   'tdb_decode12_f32': (_I, [_P, _P, _I64, _I, _I, _P]),

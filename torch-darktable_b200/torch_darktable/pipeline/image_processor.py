@@ -16,6 +16,7 @@ from beartype import beartype
 import torch
 
 import torch_darktable as td
+from torch_darktable import _lib
 from torch_darktable.extension import extension
 
 from .camera_settings import CameraSettings
@@ -380,35 +381,39 @@ class ImageProcessor:
     self._seq += 1
     ma = float(s.moving_average)
     lane.stream.wait_stream(cur)
-    with torch.cuda.stream(lane.stream):
-      rgb = td.demosaic_packed(self._strip(bytes), self.image_size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
-                               white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
-      if self._ev_bounds is not None:
-        lane.stream.wait_event(self._ev_bounds)  # the previous frame's bounds are final (and its read of the buffer written here is done)
-      smoothed, ratio = lane.frame.smooth_deferred(lane.post, rgb, True, True, prev_b, ma, out_b)
-      self._ev_bounds = torch.cuda.Event()
-      self._ev_bounds.record(lane.stream)
-      wiener = lane.wiener if s.enable_denoise else None
-      bil = lane.bil if s.enable_bilateral else None
-      image = lane.frame.prepare(smoothed, ratio, out_b, wiener)
-      if wiener is not None:
-        image = lane.frame.denoise(wiener, image, s.denoise, True, bil)
-      elif bil is not None:
-        lane.frame.bilateral_grid(bil, image)
-      lab = wiener is not None and bil is not None
-      if self._ev_metrics is not None:
-        lane.stream.wait_event(self._ev_metrics)
-      lane.frame.metrics(image, bil, s.bilateral, True, True, prev_m, ma, out_m, lab_input=lab)
-      self._ev_metrics = torch.cuda.Event()
-      self._ev_metrics.record(lane.stream)
-      params = td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
-      op, tf = _TONEMAP_OPS[s.tone_mapping], self._transform_for(image_name).name
-      if bil is not None:
-        res = lane.frame.slice_tonemap(image, bil, s.bilateral, op, out_m, params, None, tf, lab_input=s.enable_denoise, out=out)
-      else:
-        res = extension.tonemap(image, op, None if op == 'aces' else out_m, params, None, tf, out=out)
-      lane.done = torch.cuda.Event()
-      lane.done.record(lane.stream)
+    _lib.lib.tdb_set_concurrency_hint(2)  # kernels that would fill an SM's register file alone leave room for the other lane's
+    try:
+      with torch.cuda.stream(lane.stream):
+        rgb = td.demosaic_packed(self._strip(bytes), self.image_size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
+                                 white_balance=self.white_balance, ppg_median_threshold=s.ppg_median_threshold)
+        if self._ev_bounds is not None:
+          lane.stream.wait_event(self._ev_bounds)  # the previous frame's bounds are final (and its read of the buffer written here is done)
+        smoothed, ratio = lane.frame.smooth_deferred(lane.post, rgb, True, True, prev_b, ma, out_b)
+        self._ev_bounds = torch.cuda.Event()
+        self._ev_bounds.record(lane.stream)
+        wiener = lane.wiener if s.enable_denoise else None
+        bil = lane.bil if s.enable_bilateral else None
+        image = lane.frame.prepare(smoothed, ratio, out_b, wiener)
+        if wiener is not None:
+          image = lane.frame.denoise(wiener, image, s.denoise, True, bil)
+        elif bil is not None:
+          lane.frame.bilateral_grid(bil, image)
+        lab = wiener is not None and bil is not None
+        if self._ev_metrics is not None:
+          lane.stream.wait_event(self._ev_metrics)
+        lane.frame.metrics(image, bil, s.bilateral, True, True, prev_m, ma, out_m, lab_input=lab)
+        self._ev_metrics = torch.cuda.Event()
+        self._ev_metrics.record(lane.stream)
+        params = td.TonemapParameters(s.tone_gamma, s.tone_intensity, s.light_adapt, s.vibrance).to_cpp()
+        op, tf = _TONEMAP_OPS[s.tone_mapping], self._transform_for(image_name).name
+        if bil is not None:
+          res = lane.frame.slice_tonemap(image, bil, s.bilateral, op, out_m, params, None, tf, lab_input=s.enable_denoise, out=out)
+        else:
+          res = extension.tonemap(image, op, None if op == 'aces' else out_m, params, None, tf, out=out)
+        lane.done = torch.cuda.Event()
+        lane.done.record(lane.stream)
+    finally:
+      _lib.lib.tdb_set_concurrency_hint(0)
     if track and not torch.cuda.is_current_stream_capturing():
       # allocator bookkeeping across streams (track=False: the caller keeps `bytes` and the result alive until its own streams are done): the input is read on the lane, a result allocated on the lane is consumed on the caller's stream
       bytes.record_stream(lane.stream)
