@@ -64,7 +64,7 @@ def bind_host_to_gpu(index: int) -> dict:
 
 
 class HostFrameRunner:
-  def __init__(self, processor: ImageProcessor, slots: int = 3):
+  def __init__(self, processor: ImageProcessor, slots: int = ImageProcessor.LANES + 1):
     self.processor = processor
     self.device = processor.device
     self.slots = slots

@@ -41,6 +41,8 @@ _TONEMAP_OPS = {ToneMapper.reinhard: 'reinhard', ToneMapper.linear: 'linear', To
 
 @beartype
 class ImageProcessor:
+  LANES = 3  # most frames in flight through `submit` / `process_batch` / HostFrameRunner (three below 3 MP, two above: `_n_lanes`)
+
   @beartype
   def __init__(self, image_size: tuple[int, int], bayer_pattern: td.BayerPattern, packed_format: td.PackedFormat,
                settings: ImageProcessingSettings, device: torch.device, white_balance: tuple[float, float, float] | None,
@@ -61,14 +63,17 @@ class ImageProcessor:
     self._bounds_state = torch.empty(2, dtype=torch.float32, device=device)
     self._metrics_state = torch.empty(5, dtype=torch.float32, device=device)
     self._batch_graph = None  # (key, graph, static input, static output) of process_batch
-    # Two frames in flight (`submit`): consecutive frames alternate between two lanes -- a CUDA stream plus its own workspaces -- so
-    # that the tail of one frame's kernels and its single-CTA statistics steps overlap the next frame's work (measured: +9 % at 4K).
-    # The EMA chain stays sequential: frame i reads the state frame i - 1 wrote, through a ping-pong pair of device buffers
-    # ([0] = the resting buffers above) and one event per statistic.
-    self._bounds_pp = [self._bounds_state, torch.empty(2, dtype=torch.float32, device=device)]
-    self._metrics_pp = [self._metrics_state, torch.empty(5, dtype=torch.float32, device=device)]
+    # Several frames in flight (`submit`): consecutive frames rotate over LANES lanes -- a CUDA stream plus its own workspaces -- so
+    # that the tail of one frame's kernels and its single-CTA statistics steps overlap the next frames' work (measured at 4K: +9 %
+    # with two lanes, +10.5 % with three).  The EMA chain stays sequential: frame i reads the state frame i - 1 wrote, through a ring
+    # of LANES device buffers ([0] = the resting buffers above; frame i writes slot i % LANES on lane i % LANES, so the slot is next
+    # written by the frame that follows frame i on the SAME stream) and one event per statistic.
+    self._bounds_pp = [self._bounds_state] + [torch.empty(2, dtype=torch.float32, device=device) for _ in range(self.LANES - 1)]
+    self._metrics_pp = [self._metrics_state] + [torch.empty(5, dtype=torch.float32, device=device) for _ in range(self.LANES - 1)]
+    # measured on a B200 (profiles/r02_batch_graph.jsonl): 1080p 0.224 ms per frame with two lanes, 0.219 with three; 4K 0.805 / 0.815 ms
+    # (three 4K frames' working sets evict each other from L2)
+    self._n_lanes = 3 if image_size[0] * image_size[1] < 3_000_000 else 2
     self._lanes: list | None = None
-    self._seq = 0
     self._ev_bounds: torch.cuda.Event | None = None
     self._ev_metrics: torch.cuda.Event | None = None
 
@@ -320,7 +325,7 @@ class ImageProcessor:
   def _ensure_lanes(self) -> list:
     if self._lanes is None:
       s, lanes = self.settings, []
-      for k in range(2):
+      for k in range(self._n_lanes):
         lane = ImageProcessor._Lane()
         lane.stream, lane.done = torch.cuda.Stream(self.device), None
         if k == 0:  # the processor's own workspaces
@@ -350,7 +355,7 @@ class ImageProcessor:
     """Index of the ping-pong buffers that hold the latest EMA state (values set from outside are copied into the resting pair)."""
     if self.bounds is None or self.metrics is None:
       return 0
-    for k in (0, 1):
+    for k in range(self.LANES):
       if self.bounds is self._bounds_pp[k] and self.metrics is self._metrics_pp[k]:
         return k
     self._bounds_pp[0].copy_(self.bounds.to(device=self.device, dtype=torch.float32).reshape(-1))
@@ -361,10 +366,10 @@ class ImageProcessor:
   @beartype
   def submit(self, bytes: torch.Tensor, image_name: str, out: torch.Tensor | None = None, track: bool = True):
     """`process(bytes, image_name)` without waiting for the previous frame to leave the GPU (B200 addition): the frame -- its own image
-    set -- is enqueued on one of two alternating lanes (stream + workspaces), ordered after the work already queued on the current
+    set -- is enqueued on one of LANES rotating lanes (stream + workspaces), ordered after the work already queued on the current
     stream, and (result, event) is returned; the result is complete when the event is (`join()` orders the current stream after
     all frames in flight).  The bounds / metrics EMA is chained exactly as by consecutive `process` calls: frame i reads the state
-    frame i - 1 wrote (a ping-pong pair of device buffers, one event per statistic), so the results are those of the sequential calls."""
+    frame i - 1 wrote (a ring of device buffers, one event per statistic), so the results are those of the sequential calls."""
     s = self.settings
     if not (s.postprocess and s.color_smoothing_passes >= 1):  # not the fused nine-launch configuration: run in line
       res = self._process_image_set_fused({image_name: bytes}, {image_name: out} if out is not None else None)[image_name]
@@ -376,12 +381,12 @@ class ImageProcessor:
     par = self._state_parity()  # (a copy, if any, is queued on the current stream, before the lane picks it up)
     prev_b = None if self.bounds is None else self._bounds_pp[par]
     prev_m = None if self.metrics is None else self._metrics_pp[par]
-    out_b, out_m = self._bounds_pp[1 - par], self._metrics_pp[1 - par]
-    lane = lanes[self._seq & 1]
-    self._seq += 1
+    nxt = (par + 1) % self._n_lanes  # ring slot AND lane of this frame
+    out_b, out_m = self._bounds_pp[nxt], self._metrics_pp[nxt]
+    lane = lanes[nxt]
     ma = float(s.moving_average)
     lane.stream.wait_stream(cur)
-    _lib.lib.tdb_set_concurrency_hint(2)  # kernels that would fill an SM's register file alone leave room for the other lane's
+    _lib.lib.tdb_set_concurrency_hint(self._n_lanes)  # kernels that would fill an SM's register file alone leave room for the other lane's
     try:
       with torch.cuda.stream(lane.stream):
         rgb = td.demosaic_packed(self._strip(bytes), self.image_size, self.bayer_pattern, method=s.debayer.name, format_type=self.packed_format,
@@ -425,9 +430,10 @@ class ImageProcessor:
   def join(self):
     """Order the current stream after every submitted frame and bring the EMA state back to its resting buffers."""
     self._join_lanes()
-    if self.bounds is self._bounds_pp[1]:
-      self._bounds_pp[0].copy_(self._bounds_pp[1]), self._metrics_pp[0].copy_(self._metrics_pp[1])
-      self.bounds, self.metrics = self._bounds_pp[0], self._metrics_pp[0]
+    for k in range(1, self.LANES):
+      if self.bounds is self._bounds_pp[k]:
+        self._bounds_pp[0].copy_(self._bounds_pp[k]), self._metrics_pp[0].copy_(self._metrics_pp[k])
+        self.bounds, self.metrics = self._bounds_pp[0], self._metrics_pp[0]
 
   # -- batches ----------------------------------------------------------------------------------------------------
   @beartype
