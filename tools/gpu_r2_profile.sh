@@ -17,6 +17,8 @@ $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
 timeout 900 ncu --set full --metrics smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,sm__inst_executed_pipe_xu.sum \
   --clock-control none --import-source on -k 'regex:rcd3_kernel|rcd_strip_kernel|smooth_kernel|frame_stats_kernel|prepare_kernel|wiener32_kernel|wiener32_shared_kernel|wiener_normalize_kernel|grid_build_kernel|metrics_sliced_kernel|tonemap_kernel' -s 27 -c 9 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log
+python tools/bench_batch.py > gpurun_out/batch_graph_$TAG.jsonl 2> gpurun_out/batch_graph_$TAG.err
+python tools/bench_stages.py --kernels > gpurun_out/stages_ours_$TAG.jsonl 2> gpurun_out/stages_ours_$TAG.err
 python - <<P
 import json
 d=json.loads(open('gpurun_out/bench_ours_$TAG.json').read().strip().splitlines()[-1])
