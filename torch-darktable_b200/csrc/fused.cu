@@ -72,11 +72,14 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) 
   const int g1_col = fc(0, 0, a.filters) == 1 ? 0 : 1;
   if (t0 < 2 && a.counters) a.counters[t0] = 0u;
   if (kVec) {  // width % 4 == 0: a 4-pixel group stays inside one row and starts on an even column
-    const int wq = a.width >> 2;
-    for (int64_t g = t0; g < n / 4; g += stride) {
-      const int y = (int)(g / wq);
+    // the row of a group is kept incrementally (one division per thread, not a 64-bit one per group); n / 4 < 2^31
+    const unsigned wq = (unsigned)a.width >> 2, ngroups = (unsigned)(n / 4);
+    const unsigned step = (unsigned)stride, dy = step / wq, dq = step - dy * wq;
+    unsigned y = (unsigned)t0 / wq, q = (unsigned)t0 - y * wq;
+    for (unsigned g = (unsigned)t0; g < ngroups; g += step, q += dq, y += dy) {
+      if (q >= wq) q -= wq, y++;
       const bool even_row = !(y & 1);
-      const float4 *src = reinterpret_cast<const float4 *>(a.in) + 3 * g;
+      const float4 *src = reinterpret_cast<const float4 *>(a.in) + 3 * (size_t)g;
       rgb_t p[4];
       unpack4(ld_stream(src), ld_stream(src + 1), ld_stream(src + 2), p);
 #pragma unroll
@@ -86,13 +89,13 @@ __global__ void __launch_bounds__(kThreads) prepare_kernel(const PrepareArgs a) 
         float2 ab[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) ab[k] = lab_ab_and_loglum(p[k], a.eps, ll[k]);
-        float4 *dst = reinterpret_cast<float4 *>(a.out) + 2 * g;
+        float4 *dst = reinterpret_cast<float4 *>(a.out) + 2 * (size_t)g;
         dst[0] = make_float4(ab[0].x, ab[0].y, ab[1].x, ab[1].y), dst[1] = make_float4(ab[2].x, ab[2].y, ab[3].x, ab[3].y);
         reinterpret_cast<float4 *>(a.loglum)[g] = make_float4(ll[0], ll[1], ll[2], ll[3]);
       } else {
         float4 o0, o1, o2;
         pack4(p, o0, o1, o2);
-        float4 *dst = reinterpret_cast<float4 *>(a.out) + 3 * g;
+        float4 *dst = reinterpret_cast<float4 *>(a.out) + 3 * (size_t)g;
         dst[0] = o0, dst[1] = o1, dst[2] = o2;
       }
       if (a.zero) reinterpret_cast<float4 *>(a.zero)[g] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -235,6 +238,7 @@ int tdb_frame_prepare(const float *rgb, float *out, void *wiener_scratch_buf, in
                       const float *bounds, float eps, tdb_stream_t stream) {
   TDB_REQUIRE(rgb && out && bounds, "frame_prepare: null pointer");
   TDB_REQUIRE(width > 0 && height > 0, "frame_prepare: empty image");
+  TDB_REQUIRE((int64_t)width * height < ((int64_t)1 << 32), "frame_prepare: image too large (2^32 pixels)");
   TDB_REQUIRE(!wiener_scratch_buf || eps > 0.0f, "Epsilon must be positive");
   PrepareArgs a{rgb, out, nullptr, nullptr, nullptr, ratio, bounds, width, height, filters, eps};
   if (wiener_scratch_buf) {

@@ -28,6 +28,7 @@ struct SliceArgs {
   const float *grid;  // blurred bilateral grid
   bil::GridDims g;
   float sigma_s, sigma_r, detail;
+  bil::GridLimits lim;  // the grid limits as floats (bil::make_sample's float form: no int <-> float conversions per pixel)
 };
 
 // destination coordinates of source pixel (x, y); (ow, oh) = transformed size.  torch.rot90(k) is counter-clockwise.
@@ -72,9 +73,9 @@ __device__ __forceinline__ ToneConsts tone_consts(const TonemapArgs &a) {
 }
 // one pixel: [slice] -> [3x3] -> tone curve -> gamma -> vibrance -> 0x00BBGGRR
 template <int kOp, int kSlice>
-__device__ __forceinline__ uint32_t tone_pixel(rgb_t c, int x, int y, const ToneConsts &k, const SliceArgs &sl) {
-  if (kSlice == 1) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);
-  if (kSlice == 2) c = bil::slice_lab(sl.grid, x, y, c, sl.g, sl.sigma_s, sl.sigma_r, sl.detail);  // the input pixel is Lab
+__device__ __forceinline__ uint32_t tone_pixel(rgb_t c, float x, float y, const ToneConsts &k, const SliceArgs &sl) {
+  if (kSlice == 1) c = bil::slice_rgb(sl.grid, x, y, c, sl.g, sl.lim, sl.sigma_s, sl.sigma_r, sl.detail);
+  if (kSlice == 2) c = bil::slice_lab(sl.grid, x, y, c, sl.g, sl.lim, sl.sigma_s, sl.sigma_r, sl.detail);  // the input pixel is Lab
   if (k.has_matrix) c = mat3(k.m, c);
   rgb_t t;
   if (kOp == TDB_TM_ACES) {
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint32_t tone_pixel(rgb_t c, int x, int y, const Tone
   }
   const rgb_t g{powf(fmaxf(t.x, 0.0f), k.inv_gamma), powf(fmaxf(t.y, 0.0f), k.inv_gamma), powf(fmaxf(t.z, 0.0f), k.inv_gamma)};
   const rgb_t v = tm::vibrance(g, k.vibrance);
-  return tm::to_u8(v.x) | (tm::to_u8(v.y) << 8) | (tm::to_u8(v.z) << 16);
+  return tm::pack_u8(v);
 }
 
 // Transforms that keep rows as rows (none, flips, rotate_180): a thread owns four consecutive pixels of a row -- three 128-bit
@@ -103,14 +104,20 @@ __global__ void __launch_bounds__(kThreads) tonemap_rows_kernel(const float *__r
   const bool flip_y = a.transform == TDB_TF_FLIP_VERT || a.transform == TDB_TF_ROTATE_180 || a.transform == TDB_TF_TRANSVERSE;
   const int wq = width >> 2;
   const int64_t ngroups = (int64_t)wq * height;
-  for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * kThreads) {
-    const int y = (int)(g / wq), x = 4 * (int)(g - (int64_t)y * wq);
+  // row / column of a group kept incrementally: one 64-bit division per thread instead of one per group
+  const int64_t step = (int64_t)gridDim.x * kThreads, g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int dy = (int)(step / wq), dq = (int)(step - (int64_t)dy * wq);
+  int y = (int)(g0 / wq), q = (int)(g0 - (int64_t)y * wq);
+  for (int64_t g = g0; g < ngroups; g += step, q += dq, y += dy) {
+    if (q >= wq) q -= wq, y++;
+    const int x = 4 * q;
     const float4 *src = reinterpret_cast<const float4 *>(rgb) + 3 * g;
     rgb_t p[4];
     unpack4(__ldg(src), __ldg(src + 1), __ldg(src + 2), p);
     uint32_t v[4];
+    const float xf = (float)x, yf = (float)y;  // pixel coordinates < 2^24: xf + i is exact
 #pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = tone_pixel<kOp, kSlice>(p[i], x + i, y, k, sl);
+    for (int i = 0; i < 4; i++) v[i] = tone_pixel<kOp, kSlice>(p[i], xf + (float)i, yf, k, sl);
     if (flip_x) {
       const uint32_t t0 = v[0], t1 = v[1];
       v[0] = v[3], v[1] = v[2], v[2] = t1, v[3] = t0;
@@ -138,8 +145,9 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
       const float4 *src = reinterpret_cast<const float4 *>(rgb + 3 * ((int64_t)y * width + x));
       rgb_t p[4];
       unpack4(__ldg(src), __ldg(src + 1), __ldg(src + 2), p);
+      const float xf = (float)x, yf = (float)y;  // pixel coordinates < 2^24: xf + i is exact
 #pragma unroll
-      for (int i = 0; i < 4; i++) tile[ly][4 * q + i] = tone_pixel<kOp, kSlice>(p[i], x + i, y, kc, sl);
+      for (int i = 0; i < 4; i++) tile[ly][4 * q + i] = tone_pixel<kOp, kSlice>(p[i], xf + (float)i, yf, kc, sl);
     }
   } else {
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
       const int ly = ly0 + 8 * k, x = x0 + lx, y = y0 + ly;
       if (x < width && y < height) {
         const float *p = rgb + 3 * ((int64_t)y * width + x);
-        tile[ly][lx] = tone_pixel<kOp, kSlice>(rgb_t{__ldg(p), __ldg(p + 1), __ldg(p + 2)}, x, y, kc, sl);
+        tile[ly][lx] = tone_pixel<kOp, kSlice>(rgb_t{__ldg(p), __ldg(p + 1), __ldg(p + 2)}, (float)x, (float)y, kc, sl);
       }
     }
   }
@@ -180,15 +188,20 @@ __global__ void __launch_bounds__(kThreads) tonemap_kernel(const float *__restri
   };
   if ((dw & 3) == 0 && (dx0 & 3) == 0 && (ow & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
     // 32-bit stores: a destination row of the tile is dw * 3 / 4 words, each made of two neighbouring pixels
-    const int wpr = dw * 3 / 4;
-    for (int i = threadIdx.x; i < wpr * dh; i += kThreads) {
-      const int dy = i / wpr, wq = i - dy * wpr;
-      const int g = wq / 3, ph = wq - 3 * g;  // pixel group of four, word inside its twelve bytes
-      const int ox = dx0 + 4 * g + ph, oy = dy0 + dy;
-      const uint32_t va = source(ox, oy), vb = source(ox + 1, oy);
-      const uint32_t word = ph == 0 ? (va | (vb << 24)) : (ph == 1 ? ((va >> 8) | (vb << 16)) : ((va >> 16) | (vb << 8)));
-      reinterpret_cast<uint32_t *>(out + 3 * ((int64_t)oy * ow + dx0))[wq] = word;
-    }
+    auto store_words = [&](const int wpr) {
+      for (int i = threadIdx.x; i < wpr * dh; i += kThreads) {
+        const int dy = i / wpr, wq = i - dy * wpr;
+        const int g = wq / 3, ph = wq - 3 * g;  // pixel group of four, word inside its twelve bytes
+        const int ox = dx0 + 4 * g + ph, oy = dy0 + dy;
+        const uint32_t va = source(ox, oy), vb = source(ox + 1, oy);
+        const uint32_t word = ph == 0 ? (va | (vb << 24)) : (ph == 1 ? ((va >> 8) | (vb << 16)) : ((va >> 16) | (vb << 8)));
+        reinterpret_cast<uint32_t *>(out + 3 * ((int64_t)oy * ow + dx0))[wq] = word;
+      }
+    };
+    // full-width tiles (all but the last tile column): the words per row are a compile-time constant, so the division by it is a
+    // multiply-high instead of the I2F / MUFU.RCP / F2I sequence of a run-time divisor (ncu: 2 of them per stored word)
+    if (dw == kTile) store_words(kTile * 3 / 4);
+    else store_words(dw * 3 / 4);
   } else {
     for (int i = threadIdx.x; i < dw * dh; i += kThreads) {
       const int dy = i / dw, dx = i - dy * dw;
@@ -256,7 +269,7 @@ int tdb_bilateral_slice_tonemap(const float *rgb, int lab_input, const void *bil
   const bil::GridDims g = bil::grid_dims(width, height, sigma_s, sigma_r);
   // scratch layout of bilateral.cu: [splatted grid][blurred grid]
   const float *blurred = static_cast<const float *>(bilateral_scratch) + (size_t)g.x * g.y * g.z;
-  const SliceArgs sl{blurred, g, sigma_s, sigma_r, detail};
+  const SliceArgs sl{blurred, g, sigma_s, sigma_r, detail, bil::grid_limits(g)};
   if (lab_input) return launch_tonemap<2>(rgb, out, width, height, a, sl, as_stream(stream), "bilateral_slice_tonemap");
   return launch_tonemap<1>(rgb, out, width, height, a, sl, as_stream(stream), "bilateral_slice_tonemap");
 }
