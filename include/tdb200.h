@@ -77,10 +77,15 @@ int tdb_unpack12_wb(const uint8_t *packed, float *cfa, int width, int height, in
  * gains: device float[3].  in == out is allowed.                                                           */
 int tdb_white_balance(const float *in, float *out, int width, int height, uint32_t filters, const float *gains, tdb_stream_t stream);
 /* Replaces estimate_white_balance (extension.cpp:211, csrc/white_balance.cu:94-162): phase 1 collects the
- * bright-patch samples; the quantile + mean run in the shim on the compacted device arrays.
- * chroma: (n_samples,2), intensity: (n_samples), valid: (n_samples) uint8; n_samples = (W/stride)*(H/stride). */
+ * bright-patch samples of one image; phase 2 (csrc/white_balance.cu:135-161: masked gathers, torch::quantile, mean) is one
+ * single-CTA kernel over the sample arrays of all images: exact selection of the two order statistics torch.quantile
+ * interpolates between, then the mean chromaticity of the samples at or above the threshold.
+ * chroma: (n_samples,2), intensity: (n_samples), valid: (n_samples) uint8; n_samples = (W/stride)*(H/stride) per image.
+ * gains: device float[3] = (R/G, 1, B/G), or (1, 1, 1) when no sample is valid.                                        */
 int tdb_wb_collect_samples(const float *cfa, int width, int height, uint32_t filters, int stride, float *chroma,
                            float *intensity, uint8_t *valid, tdb_stream_t stream);
+int tdb_wb_estimate_gains(const float *chroma, const float *intensity, const uint8_t *valid, int64_t n_samples, float quantile,
+                          float *gains, tdb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Demosaic.  cfa (H,W) -> rgb (H,W,3).  width and height must be even and >= 16.

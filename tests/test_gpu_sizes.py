@@ -184,6 +184,51 @@ def test_estimate_white_balance(pattern):
   np.testing.assert_allclose(got, 1.0 / gains, rtol=0.02)  # the estimate is the cast (R/G, 1, B/G) of the neutral scene
 
 
+@pytest.mark.parametrize('quantile', [0.0, 0.5, 0.95, 0.98, 1.0])
+def test_estimate_white_balance_matches_the_torch_formulation(quantile):
+  """The selection kernel (tdb_wb_estimate_gains) against the reference's own composition of the second phase
+  (white_balance.cu:135-161: masked gather, torch.quantile, masked gather, mean) on the sample arrays of the first phase, incl. the
+  quantile's float32 rank arithmetic; saturated patches make about a fifth of the samples invalid."""
+  import torch
+  import torch_darktable as td
+  from torch_darktable import _lib
+  from torch_darktable.extension import _filters
+  dev = torch.device('cuda:0')
+  h, w, stride = 776, 1032, 8
+  images = []
+  for seed in (3, 4, 5):
+    cfa = synth.mosaic(synth.scene_rgb(h, w, seed), 'RGGB') * 1.6  # pushes the highlights beyond 1: invalid samples
+    images.append(torch.from_numpy(np.ascontiguousarray(cfa, np.float32)).to(dev))
+  got = td.estimate_white_balance(images, td.BayerPattern.RGGB, quantile, stride)
+  sh, sw = h // stride, w // stride
+  n = sh * sw
+  chroma = torch.empty((3 * n, 2), dtype=torch.float32, device=dev)
+  inten = torch.empty(3 * n, dtype=torch.float32, device=dev)
+  valid = torch.empty(3 * n, dtype=torch.uint8, device=dev)
+  for i, img in enumerate(images):
+    rc = _lib.lib.tdb_wb_collect_samples(img.data_ptr(), w, h, _filters(td.BayerPattern.RGGB.value),
+                                         stride, chroma[i * n:].data_ptr(), inten[i * n:].data_ptr(), valid[i * n:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+  mask = valid.bool()
+  assert 0.02 < 1.0 - mask.float().mean().item() < 0.9
+  c, v = chroma[mask], inten[mask]
+  bright = c[v >= torch.quantile(v, quantile)]
+  mean = bright.mean(0)
+  want = torch.stack((mean[0] / mean[1], torch.tensor(1.0, device=dev), (1.0 - mean[0] - mean[1]) / mean[1]))
+  np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-6)
+  assert int((v >= torch.quantile(v, quantile)).sum()) >= 1
+
+
+def test_estimate_white_balance_without_valid_samples():
+  """every 2x2 patch saturated -> (1, 1, 1) (white_balance.cu:143-145); an image smaller than the stride has no sample site at all"""
+  import torch
+  import torch_darktable as td
+  dev = torch.device('cuda:0')
+  img = torch.full((64, 96, 1), 1.5, dtype=torch.float32, device=dev)
+  assert td.estimate_white_balance([img], td.BayerPattern.RGGB, 0.95, 8).cpu().tolist() == [1.0, 1.0, 1.0]
+  assert td.estimate_white_balance([img[:4, :4]], td.BayerPattern.RGGB, 0.95, 8).cpu().tolist() == [1.0, 1.0, 1.0]
+
+
 @pytest.mark.parametrize('h,w', [(516, 1100), (1030, 700), (250, 372)])
 @pytest.mark.parametrize('sigma,shadows,highlights,clarity', [(0.2, 1.0, 1.0, 0.0), (0.3, 1.4, 0.7, 0.25)])
 def test_laplacian(impl, oracle, sigma, shadows, highlights, clarity, h, w):

@@ -6,7 +6,10 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
 t0=$(date +%s)
-timeout 900 python -m pytest tests -m gpu -q -n 4 > gpurun_out/pytest_gpu_$TAG.log 2>&1
+# PYTEST_ARGS: a test selection instead of the whole suite (e.g. "tests/test_gpu_sizes.py -k white_balance"); "none" skips the tests
+if [ "$PYTEST_ARGS" = none ]; then echo skipped > gpurun_out/pytest_gpu_$TAG.log; else
+timeout 900 python -m pytest ${PYTEST_ARGS:-tests} -m gpu -q -n 4 > gpurun_out/pytest_gpu_$TAG.log 2>&1
+fi
 rc=$?
 echo "xdist rc=$rc in $(( $(date +%s) - t0 )) s" | tee -a gpurun_out/pytest_gpu_$TAG.log
 tail -4 gpurun_out/pytest_gpu_$TAG.log

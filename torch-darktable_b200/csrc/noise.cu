@@ -7,7 +7,7 @@
 //                             (four 8-bit passes over the samples, shared-memory histogram), then the same selection on |r - median|.
 // torch.median returns the LOWER of the two middle values for an even count: rank (n - 1) / 2 of the sorted samples; so does this.
 // The result stays on the device (3 floats) and can feed Wiener.process as its noise tensor without a host round trip.
-#include "tdb_common.cuh"
+#include "select.cuh"
 
 namespace tdb {
 namespace {
@@ -32,46 +32,13 @@ __global__ void __launch_bounds__(kThreads) laplacian_samples_kernel(const float
   }
 }
 
-__device__ __forceinline__ uint32_t ordered_key(float v) {
-  const uint32_t u = __float_as_uint(v);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_value(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
-
-// value of rank `rank` (0-based) among f(v[i]), i < n; all threads of the CTA call it and receive the result
-template <class F>
-__device__ float select_rank(const float *__restrict__ v, int64_t n, int64_t rank, F f, uint32_t *hist, uint32_t *pick) {
-  uint32_t prefix = 0, mask = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
-    __syncthreads();
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t k = ordered_key(f(v[i]));
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t acc = 0, b = 0;
-      for (; b < 256; b++) {
-        if (acc + hist[b] > rank) break;
-        acc += hist[b];
-      }
-      pick[0] = b, pick[1] = acc;
-    }
-    __syncthreads();
-    prefix |= pick[0] << shift, mask |= 255u << shift;
-    rank -= pick[1];
-    __syncthreads();
-  }
-  return key_value(prefix);
-}
-
 __global__ void __launch_bounds__(kSelectThreads) mad_select_kernel(const float *__restrict__ resp, int64_t n, float *__restrict__ sigma) {
   __shared__ uint32_t hist[256], pick[2];
   const float *v = resp + (int64_t)blockIdx.x * n;
   const int64_t rank = (n - 1) / 2;
-  const float med = select_rank(v, n, rank, [](float x) { return x; }, hist, pick);
-  const float mad = select_rank(v, n, rank, [med](float x) { return fabsf(x - med); }, hist, pick);
+  auto all = [](int64_t) { return true; };
+  const float med = sel::select_rank(n, rank, [v](int64_t i) { return v[i]; }, all, hist, pick);
+  const float mad = sel::select_rank(n, rank, [v, med](int64_t i) { return fabsf(v[i] - med); }, all, hist, pick);
   if (threadIdx.x == 0) sigma[blockIdx.x] = __fdiv_rn(mad, 0.6745f);  // IEEE division like torch's (the library is built with fast-math)
 }
 

@@ -4,6 +4,7 @@
 // launch one thread per pixel with scalar 4-byte accesses to interleaved RGB on the legacy default stream and device-
 // synchronise after every op.  Here a thread owns four pixels (48 bytes = three 128-bit accesses), kernels are
 // grid-stride over a machine-sized grid, and every scalar the reference reads back to the host stays on the device.
+#include "select.cuh"
 #include <cfloat>
 
 #include "color_math.cuh"
@@ -198,6 +199,69 @@ __global__ void wb_collect_kernel(const float *__restrict__ cfa, int width, int 
   valid[idx] = fmaxf(fmaxf(p00, p01), fmaxf(p10, p11)) < 1.0f;
 }
 
+// The rest of estimate_white_balance (reference white_balance.cu:135-161: boolean-mask gathers, torch::quantile -- a full sort --,
+// a second masked gather and a mean, about ten library launches and two device-side compactions) in ONE single-CTA kernel over the
+// sample arrays: count the valid samples, find the two order statistics torch.quantile interpolates between by exact radix
+// selection (select.cuh), and average the chromaticity of the samples at or above the threshold.
+//   torch.quantile(v, q), linear: rank = q * (n - 1) in the dtype of v (float32), lo = floor(rank), hi = ceil(rank),
+//   result = lerp(sorted[lo], sorted[hi], rank - lo) with ATen's lerp (w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)).
+// gains = (mean_r / mean_g, 1, (1 - mean_r - mean_g) / mean_g), or (1, 1, 1) when nothing is valid.  IEEE operations throughout
+// (the library is built with fast-math; the reference's ATen kernels are not).
+constexpr int kWbThreads = 1024;
+__global__ void __launch_bounds__(kWbThreads) wb_finish_kernel(const float *__restrict__ chroma, const float *__restrict__ intensity,
+                                                                const uint8_t *__restrict__ valid, int64_t n, float quantile,
+                                                                float *__restrict__ gains) {
+  __shared__ uint32_t hist[256], pick[2];
+  __shared__ double red[3][kWbThreads / 32];
+  __shared__ double total[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto block_sum3 = [&](double a, double b, double c) {  // -> total[0..2], visible to every thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o), b += __shfl_xor_sync(0xffffffffu, b, o), c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();  // the previous round's readers of total[] are done
+    if (lane == 0) red[0][warp] = a, red[1][warp] = b, red[2][warp] = c;
+    __syncthreads();
+    if (tid < 3) {
+      double s = 0.0;
+      for (int w = 0; w < kWbThreads / 32; w++) s += red[tid][w];
+      total[tid] = s;
+    }
+    __syncthreads();
+  };
+  double cnt = 0.0;
+  for (int64_t i = tid; i < n; i += kWbThreads) cnt += valid[i] ? 1.0 : 0.0;
+  block_sum3(cnt, 0.0, 0.0);
+  const int64_t nv = (int64_t)total[0];
+  if (nv == 0) {
+    if (tid < 3) gains[tid] = 1.0f;
+    return;
+  }
+  const float rank = __fmul_rn(quantile, (float)(nv - 1));
+  const float below = floorf(rank), above = ceilf(rank);
+  const int64_t lo = min((int64_t)below, nv - 1), hi = min((int64_t)above, nv - 1);
+  auto value = [intensity](int64_t i) { return intensity[i]; };
+  auto keep = [valid](int64_t i) { return valid[i] != 0; };
+  const float a = sel::select_rank(n, lo, value, keep, hist, pick);
+  const float b = hi == lo ? a : sel::select_rank(n, hi, value, keep, hist, pick);
+  const float w = __fsub_rn(rank, below), d = __fsub_rn(b, a);
+  const float thr = w < 0.5f ? __fadd_rn(a, __fmul_rn(w, d)) : __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, w)));
+  double sr = 0.0, sg = 0.0, m = 0.0;
+  for (int64_t i = tid; i < n; i += kWbThreads) {
+    if (valid[i] && intensity[i] >= thr) sr += (double)chroma[2 * i], sg += (double)chroma[2 * i + 1], m += 1.0;
+  }
+  block_sum3(sr, sg, m);
+  if (tid == 0) {
+    if (total[2] == 0.0) {
+      gains[0] = gains[1] = gains[2] = 1.0f;
+    } else {
+      const float mr = (float)(total[0] / total[2]), mg = (float)(total[1] / total[2]);
+      gains[0] = __fdiv_rn(mr, mg), gains[1] = 1.0f, gains[2] = __fdiv_rn(__fsub_rn(__fsub_rn(1.0f, mr), mg), mg);
+    }
+  }
+}
+
 // ---- image statistics ----------------------------------------------------------------------------------------------
 __global__ void init2_kernel(float *p, float a, float b) { p[0] = a, p[1] = b; }
 __global__ void zero_kernel(float *p, int n) {
@@ -353,6 +417,14 @@ int tdb_wb_collect_samples(const float *cfa, int width, int height, uint32_t fil
   dim3 block(16, 16), grid(div_up(sw, 16), div_up(sh, 16));
   wb_collect_kernel<<<grid, block, 0, as_stream(stream)>>>(cfa, width, height, filters, stride, chroma, intensity, valid);
   return check_launch("wb_collect_samples");
+}
+
+int tdb_wb_estimate_gains(const float *chroma, const float *intensity, const uint8_t *valid, int64_t n, float quantile, float *gains,
+                          tdb_stream_t stream) {
+  TDB_REQUIRE(chroma && intensity && valid && gains, "estimate_white_balance: null pointer");
+  TDB_REQUIRE(n >= 0, "estimate_white_balance: negative sample count");
+  wb_finish_kernel<<<1, kWbThreads, 0, as_stream(stream)>>>(chroma, intensity, valid, n, quantile, gains);
+  return check_launch("wb_estimate_gains");
 }
 
 int tdb_bounds_init(float *bounds, tdb_stream_t stream) {

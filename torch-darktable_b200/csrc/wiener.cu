@@ -881,7 +881,14 @@ int run_tiles_shared(const float *in, float *acc, int width, int height, int cha
     return e ? atoi(e) : -1;
   }();
   const int regs = forced_regs >= 0 ? forced_regs : (concurrent_lanes() > 1 ? 104 : 0);
-  const int grid = a.total_steps < ctas * kNumSMs ? a.total_steps : ctas * kNumSMs;
+  // CTAs per SM of the (persistent, statically split) grid while another frame is in flight: TDB_WIENER_LANE_CTAS=1 leaves half of
+  // every SM to the other lane's kernels for the whole launch instead of only at its tail (A/B runs)
+  static const int lane_ctas = [] {
+    const char *e = getenv("TDB_WIENER_LANE_CTAS");
+    return e && atoi(e) == 1 ? 1 : 0;
+  }();
+  const int per_sm = lane_ctas && concurrent_lanes() > 1 ? lane_ctas : ctas;
+  const int grid = a.total_steps < per_sm * kNumSMs ? a.total_steps : per_sm * kNumSMs;
   if (regs == 96) shr::wiener32_shared_kernel_capped<96><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   else if (regs == 104) shr::wiener32_shared_kernel_capped<104><<<grid, kThreads, shr::kSmemBytes, s>>>(a);
   else if (ctas == 3) shr::wiener32_shared_kernel<3><<<grid, kThreads, shr::kSmemBytes, s>>>(a);

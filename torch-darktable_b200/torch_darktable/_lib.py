@@ -37,6 +37,7 @@ _SIGNATURES = {
   'tdb_unpack12_wb': (_I, [_P, _P, _I, _I, _I, _U32, _F, _P, _P]),
   'tdb_white_balance': (_I, [_P, _P, _I, _I, _U32, _P, _P]),
   'tdb_wb_collect_samples': (_I, [_P, _I, _I, _U32, _I, _P, _P, _P, _P]),
+  'tdb_wb_estimate_gains': (_I, [_P, _P, _P, _I64, _F, _P, _P]),
   'tdb_bilinear5x5': (_I, [_P, _P, _I, _I, _U32, _P]),
   'tdb_ppg': (_I, [_P, _P, _I, _I, _U32, _F, _P]),
   'tdb_rcd': (_I, [_P, _P, _I, _I, _U32, _P]),

@@ -262,6 +262,8 @@ def estimate_white_balance(bayer_images, pattern, quantile: float = 0.95, stride
   sh, sw = height // stride, width // stride
   device = first.device
   n = len(bayer_images) * sh * sw
+  if n == 0:  # no sample site at all (an image smaller than the stride): the reference's empty-selection answer
+    return torch.ones(3, dtype=torch.float32, device=device)
   chroma = torch.empty((n, 2), dtype=torch.float32, device=device)
   intensity = torch.empty(n, dtype=torch.float32, device=device)
   valid = torch.empty(n, dtype=torch.uint8, device=device)
@@ -272,16 +274,9 @@ def estimate_white_balance(bayer_images, pattern, quantile: float = 0.95, stride
       o = i * sh * sw
       check(lib.tdb_wb_collect_samples(_ptr(src), width, height, _filters(pattern), stride, _ptr(chroma[o:]), _ptr(intensity[o:]),
                                        _ptr(valid[o:]), _stream(device)))
-  ones = torch.ones(3, dtype=torch.float32, device=device)
-  mask = valid.bool()
-  chroma, intensity = chroma[mask], intensity[mask]
-  if chroma.size(0) == 0:
-    return ones
-  bright = chroma[intensity >= torch.quantile(intensity, quantile)]
-  if bright.size(0) == 0:
-    return ones
-  mean = bright.mean(0)
-  return torch.stack((mean[0] / mean[1], torch.tensor(1.0, device=device), (1.0 - mean[0] - mean[1]) / mean[1]))
+    gains = torch.empty(3, dtype=torch.float32, device=device)
+    check(lib.tdb_wb_estimate_gains(_ptr(chroma), _ptr(intensity), _ptr(valid), n, float(quantile), _ptr(gains), _stream(device)))
+  return gains
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -73,6 +73,8 @@ class ImageProcessor:
     # measured on a B200 (profiles/r02_batch_graph.jsonl): 1080p 0.224 ms per frame with two lanes, 0.219 with three; 4K 0.805 / 0.815 ms
     # (three 4K frames' working sets evict each other from L2)
     self._n_lanes = 3 if image_size[0] * image_size[1] < 3_000_000 else 2
+    if os.environ.get('TDB_LANES'):  # A/B runs
+      self._n_lanes = max(1, min(self.LANES, int(os.environ['TDB_LANES'])))
     self._lanes: list | None = None
     self._ev_bounds: torch.cuda.Event | None = None
     self._ev_metrics: torch.cuda.Event | None = None
