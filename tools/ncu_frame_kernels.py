@@ -14,7 +14,7 @@ import sys
 
 NAMES = {'rcd3_kernel': 'rcd_demosaic', 'rcd_strip_kernel': 'rcd_demosaic', 'smooth_kernel': 'color_smoothing', 'frame_stats_kernel': 'frame_stats',
          'prepare_kernel': 'frame_prepare', 'wiener32_kernel': 'wiener_tiles', 'wiener32_shared_kernel': 'wiener_tiles',
-         'wiener_normalize_kernel': 'wiener_normalize_lum', 'grid_build_kernel': 'bilateral_grid_build',
+         'wiener_normalize_kernel': 'wiener_normalize_lum', 'wiener_normalize_lum4_kernel': 'wiener_normalize_lum', 'grid_build_kernel': 'bilateral_grid_build',
          'metrics_sliced_kernel': 'metrics_sliced', 'tonemap_kernel': 'bilateral_slice_tonemap'}
 COLS = {
   'time_us': 'gpu__time_duration.sum', 'dram_read': 'dram__bytes_read.sum', 'dram_write': 'dram__bytes_write.sum',
