@@ -15,6 +15,14 @@ namespace tdb {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
+// MUFU.RCP: what a / b compiles to under --use_fast_math is a * rcp_approx(b); written out where the reciprocal of a loop
+// invariant should be taken once (bit-identical to the division it replaces)
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);  // cudaGetLastError() -> TDB_OK / TDB_ECUDA, bumps the launch counter

@@ -740,11 +740,6 @@ __global__ void __launch_bounds__(256) wiener_normalize_kernel(const NormArgs a)
 // of two) applied as a bit mask, and 1 / (mask + eps) read from a stride x stride shared table filled with the very MUFU.RCP the
 // per-pixel division compiled to -- ncu counted 215 instructions and 26 XU operations per pixel in the scalar kernel, a third of
 // them index arithmetic.  Same arithmetic per pixel, bit-identical output.  Requires width % 4 == 0 and 16-byte aligned planes.
-__device__ __forceinline__ float rcp_approx(float v) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-  return r;
-}
 template <bool kSplat, bool kAb>
 __global__ void __launch_bounds__(256) wiener_normalize_lum4_kernel(const NormArgs a, const bool lum_aligned) {
   __shared__ float m1[16];       // 1-D mask factor per phase: sum_j win[r + j*stride]^2
